@@ -1,0 +1,456 @@
+"""Fused-step engine: the CGSchNet force field (+ priors) and the BAOAB Langevin update as a fixed
+sequence of sm_100a kernel launches over pre-allocated HBM buffers, replayable as one CUDA graph.
+
+This is the fast path behind `LangevinSimulation.timestep` / `SumOut.forward` (reference call
+stack: simulation/langevin.py:101-179 -> simulation/base.py:821-909 -> models/gradients.py:72-152,
+227-290 -> models/schnet.py:177-369).  It replaces autograd by an explicit analytic backward:
+
+  forward                                   backward (weights frozen, only dE/dpos)
+  -------                                   --------
+  radius graph -> sorted CSR, d_e           F_i = sum_{e in seg(i)} (g_d[e] + g_d[rev e]) u_e
+  h0 = Emb[types]                           g_h <- g_h + g_a W1
+  per block: a = h W1^T                     g_a = CFConv(g_m, W)          (same kernel, symmetric list)
+     t = tanh(rbf Wf0^T + b), W = t Wf1^T   g_W = g_m[src] a[dst] C ; g_t = (g_W Wf1)(1-t^2) ; g_rbf = g_t Wf0
+     m = CFConv(a, W)                       g_d += sum_k g_rbf drbf_k/dd + C'(d) sum_f g_m a W   (exact)
+     c = tanh(m W2^T + b2)                  g_m = ((g_h Wl)(1-c^2)) W2
+     h = h + c Wl^T + bl
+  e_atom = MLP_out(h); E_b = sum e_atom     g_h = dE/dh through MLP_out
+
+Because radius_graph's list is symmetric and sorted centre-major / neighbour-ascending, the
+"dst-major" CSR of the reference is the same list read through the reverse-edge map, and
+W(e) == W(rev e) bit-for-bit, so BOTH CFConv directions stream the filter rows contiguously:
+m[i] = sum_{e in seg(i)} a[dst_e] W_e C_e.  No permutation gather, no atomics, deterministic.
+
+Edge buffers have a fixed capacity; the live edge count stays on the device (`seg_ptr[N]`), so a
+step has no host synchronisation and can be captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+# ------------------------------------------------------------------------------------------------
+# flat weights
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class SchNetWeights:
+    """Device-resident flat weights.  `tensors` uses nn.Linear layout [out, in] and the key names of
+    `oracle`-independent golden files: embedding, b{l}.lin1_w, b{l}.f0_w, b{l}.f0_b, b{l}.f1_w,
+    b{l}.lin2_w, b{l}.lin2_b, b{l}.lin_w, b{l}.lin_b, out{i}_w, out{i}_b."""
+    tensors: Dict[str, torch.Tensor]
+    num_blocks: int
+    num_out_layers: int
+    cutoff: float
+    num_rbf: int
+    rbf_lower: float = 0.0
+
+    def __post_init__(self):
+        t = self.tensors
+        dev = t["embedding"].device
+        self.device = dev
+        self.hidden = t["embedding"].shape[1]
+        self.filters = t["b0.f0_w"].shape[0]
+        # RBF parameters exactly as GaussianBasis._initial_params (reference radial_basis/gaussian.py:64-75)
+        centers = torch.linspace(self.rbf_lower, self.cutoff, self.num_rbf)
+        self.gamma = float(-0.5 / (centers[1] - centers[0]) ** 2)
+        self.centers = centers.to(dev).float().contiguous()
+        k: Dict[str, torch.Tensor] = {}
+        for name, w in t.items():
+            if w is None:
+                continue
+            w = w.detach().to(dev).float().contiguous()
+            k[name] = w                                   # [out,in]  == [K',N'] for the backward GEMM
+            if name.endswith("_w"):
+                k[name + "T"] = w.t().contiguous()        # [in,out]  == [K,N] for the forward GEMM
+        # fp16 copies for the W16A16 path (reference models/gptq.py:176-184: plain .half() cast)
+        for name in list(k.keys()):
+            if ".f0_" in name or ".f1_" in name or name.startswith("out"):
+                k[name + ".h"] = k[name].half().contiguous()
+        self.k = k
+        self.ones_col = None
+
+    @staticmethod
+    def from_flat(tensors: Dict[str, torch.Tensor], cutoff: float, num_rbf: int, device) -> "SchNetWeights":
+        nb = len([n for n in tensors if n.endswith(".lin1_w")])
+        no = len([n for n in tensors if n.startswith("out") and n.endswith("_w")])
+        tt = {n: (torch.as_tensor(v).to(device) if v is not None else None) for n, v in tensors.items()}
+        return SchNetWeights(tt, nb, no, float(cutoff), int(num_rbf))
+
+
+@dataclass
+class PriorTerm:
+    kind: int                      # L.PRIOR_*
+    mapping: torch.Tensor          # [order, n_terms] int32
+    mapping_batch: torch.Tensor    # [n_terms] int32
+    p0: torch.Tensor
+    p1: Optional[torch.Tensor] = None
+    p2: Optional[torch.Tensor] = None
+    n_degs: int = 1
+
+    @property
+    def n_terms(self):
+        return self.mapping.shape[1]
+
+
+# ------------------------------------------------------------------------------------------------
+# force field
+# ------------------------------------------------------------------------------------------------
+
+
+class ForceField:
+    """energy [B], forces [N,3] = f(pos) for SchNet (+ priors), all buffers pre-allocated."""
+
+    def __init__(self, weights: Optional[SchNetWeights], priors: List[PriorTerm], atom_types: torch.Tensor,
+                 mol_ptr: torch.Tensor, precision: str = "fp32", exact_cutoff_grad: bool = True,
+                 edge_capacity: Optional[int] = None, max_num_neighbors: int = 1000):
+        L.load()
+        assert precision in ("fp32", "w16a16")
+        self.w = weights
+        self.priors = priors
+        self.precision = precision
+        self.exact = bool(exact_cutoff_grad)
+        self.max_nn = int(max_num_neighbors)
+        dev = atom_types.device
+        if dev.type != "cuda":
+            raise RuntimeError("flashmd.engine.ForceField needs CUDA tensors (no CPU fallback)")
+        self.device = dev
+        self.N = int(atom_types.numel())
+        self.B = int(mol_ptr.numel() - 1)
+        self.types = atom_types.to(torch.int32).contiguous()
+        self.mol_ptr = mol_ptr.to(torch.int32).contiguous()
+        sizes = (mol_ptr[1:] - mol_ptr[:-1])
+        self.max_mol = int(sizes.max().item()) if self.B > 0 else 0
+        N, B = self.N, self.B
+        f32, i32 = torch.float32, torch.int32
+        self.energy = torch.zeros(B, dtype=f32, device=dev)
+        self.forces = torch.zeros((N, 3), dtype=f32, device=dev)
+        self.energy_terms: Dict[str, torch.Tensor] = {}
+        if weights is None:
+            return
+        F, R = weights.filters, weights.num_rbf
+        H = weights.hidden
+        assert F % 4 == 0 and H % 4 == 0
+        if edge_capacity is None:
+            # worst case: every pair inside each molecule (bounded by max_num_neighbors)
+            per = torch.clamp(sizes - 1, max=self.max_nn).to(torch.int64) * sizes.to(torch.int64)
+            edge_capacity = int(per.sum().item())
+        self.cap = cap = max(int(edge_capacity), 1)
+        wdt = torch.float16 if precision == "w16a16" else f32
+        self.deg = torch.zeros(N, dtype=i32, device=dev)
+        self.seg_ptr = torch.zeros(N + 1, dtype=i32, device=dev)
+        self.n_edges_dev = self.seg_ptr[N:]                      # int32[1] view: live edge count
+        self.scan_ws = torch.zeros(N // 1024 + 4, dtype=i32, device=dev)
+        self.src = torch.zeros(cap, dtype=i32, device=dev)
+        self.dst = torch.zeros(cap, dtype=i32, device=dev)
+        self.rev = torch.zeros(cap, dtype=i32, device=dev)
+        self.dist = torch.zeros(cap, dtype=f32, device=dev)
+        self.rbf = torch.zeros((cap, R), dtype=f32, device=dev)
+        nb = weights.num_blocks
+        self.t = [torch.zeros((cap, F), dtype=wdt, device=dev) for _ in range(nb)]
+        self.W = [torch.zeros((cap, F), dtype=wdt, device=dev) for _ in range(nb)]
+        self.gW = torch.zeros((cap, F), dtype=wdt, device=dev)
+        self.gT = torch.zeros((cap, F), dtype=wdt, device=dev)
+        self.g_rbf = torch.zeros((cap, R), dtype=f32, device=dev)
+        self.g_d = torch.zeros(cap, dtype=f32, device=dev)
+        self.h = [torch.zeros((N, H), dtype=f32, device=dev) for _ in range(nb + 1)]
+        self.a = [torch.zeros((N, F), dtype=f32, device=dev) for _ in range(nb)]
+        self.m = torch.zeros((N, F), dtype=f32, device=dev)
+        self.c = [torch.zeros((N, H), dtype=f32, device=dev) for _ in range(nb)]
+        self.g_h = [torch.zeros((N, H), dtype=f32, device=dev) for _ in range(2)]
+        self.g_c = torch.zeros((N, H), dtype=f32, device=dev)
+        self.g_m = torch.zeros((N, F), dtype=f32, device=dev)
+        self.g_a = torch.zeros((N, F), dtype=f32, device=dev)
+        odt = torch.float16 if precision == "w16a16" else f32
+        widths = [weights.tensors[f"out{i}_w"].shape[0] for i in range(weights.num_out_layers)]
+        self.y = [torch.zeros((N, wd), dtype=(odt if i < len(widths) - 1 else f32), device=dev)
+                  for i, wd in enumerate(widths)]
+        self.g_y = [torch.zeros((N, wd), dtype=odt, device=dev) for wd in widths[:-1]]
+        self.ones = torch.ones((N, 1), dtype=odt, device=dev)
+        self.e_schnet = torch.zeros(B, dtype=f32, device=dev)
+        self.launches_per_eval = 0
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _lin(self, x, w, bias, y, m_dev=None, **kw):
+        M, K = x.shape
+        N = w.shape[1]
+        L.call("fmd_linear", L.ptr(x), L.dt_code(x), L.ptr(w), L.dt_code(w), L.ptr(bias), L.ptr(y), L.dt_code(y), M, N,
+               K, L.ptr(m_dev), kw.get("pro_act", 0), int(kw.get("x_round", False)), kw.get("epi_act", 0),
+               L.ptr(kw.get("aux")), L.dt_code(kw["aux"]) if kw.get("aux") is not None else 0, L.ptr(kw.get("res")),
+               self._st)
+        self._n += 1
+
+    def _cfconv(self, x, W, out):
+        L.call("fmd_cfconv_csr", L.ptr(x), L.ptr(W), L.dt_code(W), L.ptr(self.dist), L.ptr(self.dst),
+               L.ptr(self.seg_ptr), None, 4, self.N, self.cap, x.shape[1], self.w.cutoff, L.ptr(out), self._st)
+        self._n += 1
+
+    # -- neighbour list --------------------------------------------------------------------------
+    def build_neighbor_list(self, pos):
+        st, w = self._st, self.w
+        L.call("fmd_nl_count", L.ptr(pos), L.ptr(self.mol_ptr), self.B, self.N, self.max_mol, w.cutoff, self.max_nn,
+               L.ptr(self.deg), st)
+        L.call("fmd_exclusive_scan_i32", L.ptr(self.deg), L.ptr(self.seg_ptr), self.N, L.ptr(self.scan_ws), st)
+        L.call("fmd_nl_fill", L.ptr(pos), L.ptr(self.mol_ptr), self.B, self.N, self.max_mol, w.cutoff, self.max_nn,
+               L.ptr(self.seg_ptr), self.cap, L.ptr(self.src), L.ptr(self.dst), 4, L.ptr(self.dist), st)
+        L.call("fmd_nl_reverse", L.ptr(self.seg_ptr), L.ptr(self.src), L.ptr(self.dst), 4, self.N, self.cap,
+               L.ptr(self.rev), st)
+        self._n += 6
+
+    def num_edges(self) -> int:
+        """Host read of the live edge count (synchronises)."""
+        return int(self.n_edges_dev.item())
+
+    # -- SchNet ----------------------------------------------------------------------------------
+    def _schnet(self, pos):
+        w, k, st = self.w, self.w.k, self._st
+        w16 = self.precision == "w16a16"
+        nb, ned = w.num_blocks, self.n_edges_dev
+        self.build_neighbor_list(pos)
+        # rbf [E,R] (distances were written by the neighbour-list fill)
+        L.call("fmd_dist_rbf_cutoff_fwd", L.ptr(pos), L.ptr(self.src), L.ptr(self.dst), 4, self.cap, L.ptr(ned),
+               L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, None, L.ptr(self.rbf), st)
+        L.call("fmd_embedding", L.ptr(k["embedding"]), L.ptr(self.types), 4, self.N, w.hidden, L.ptr(self.h[0]), st)
+        self._n += 2
+        tanh_f = L.ACT_TANH_CLAMPED if w16 else L.ACT_TANH
+        sfx = ".h" if w16 else ""
+        for l in range(nb):
+            self._lin(self.h[l], k[f"b{l}.lin1_wT"], None, self.a[l])
+            self._lin(self.rbf, k[f"b{l}.f0_wT{sfx}"], k[f"b{l}.f0_b{sfx}"], self.t[l], m_dev=ned, x_round=w16,
+                      epi_act=tanh_f)
+            self._lin(self.t[l], k[f"b{l}.f1_wT{sfx}"], None, self.W[l], m_dev=ned)
+            self._cfconv(self.a[l], self.W[l], self.m)
+            self._lin(self.m, k[f"b{l}.lin2_wT"], k[f"b{l}.lin2_b"], self.c[l], epi_act=L.ACT_TANH)
+            self._lin(self.c[l], k[f"b{l}.lin_wT"], k[f"b{l}.lin_b"], self.h[l + 1], res=self.h[l])
+        # output network
+        no = w.num_out_layers
+        x = self.h[nb]
+        for i in range(no):
+            last = i == no - 1
+            b = k.get(f"out{i}_b{sfx}")
+            self._lin(x, k[f"out{i}_wT{sfx}"], b, self.y[i], x_round=(w16 and x.dtype == torch.float32),
+                      epi_act=(L.ACT_NONE if last else tanh_f))
+            x = self.y[i]
+        assert self.y[-1].shape[1] == 1
+        L.call("fmd_segment_sum", L.ptr(self.y[-1]), L.ptr(self.mol_ptr), self.B, L.ptr(self.e_schnet), 0, st)
+        self._n += 1
+        # ---------------- backward
+        # dE/d(e_atom) = 1  ->  through the output MLP
+        g = self.ones
+        for i in range(no - 1, 0, -1):
+            # g_y[i-1] = (g @ out_i_w[out,in]) * (1 - y[i-1]^2)
+            self._lin(g, k[f"out{i}_w{sfx}"], None, self.g_y[i - 1], aux=self.y[i - 1], x_round=(w16 and g.dtype == torch.float32))
+            g = self.g_y[i - 1]
+        gh_cur, gh_nxt = self.g_h[0], self.g_h[1]
+        self._lin(g, k[f"out0_w{sfx}"], None, gh_cur, x_round=(w16 and g.dtype == torch.float32))
+        self.g_d.zero_()
+        self._n += 1
+        for l in range(nb - 1, -1, -1):
+            # h_{l+1} = h_l + c Wl^T + bl ; c = tanh(m W2^T + b2)
+            self._lin(gh_cur, k[f"b{l}.lin_w"], None, self.g_c, aux=self.c[l])
+            self._lin(self.g_c, k[f"b{l}.lin2_w"], None, self.g_m)
+            # m[i] = sum_{e in seg(i)} a[dst_e] W_e C_e
+            self._cfconv(self.g_m, self.W[l], self.g_a)
+            L.call("fmd_cfconv_grad_filter", L.ptr(self.g_m), L.ptr(self.a[l]), L.ptr(self.dist), L.ptr(self.src),
+                   L.ptr(self.dst), 4, self.cap, L.ptr(ned), w.filters, w.cutoff, L.ptr(self.gW), L.dt_code(self.gW),
+                   L.ptr(self.W[l]) if self.exact else None, L.dt_code(self.W[l]),
+                   L.ptr(self.g_d) if self.exact else None, 1, st)
+            self._n += 1
+            # g_t = (g_W @ f1_w[f,j]) * (1 - t^2) ; g_rbf = g_t @ f0_w[j,k]
+            self._lin(self.gW, k[f"b{l}.f1_w{sfx}"], None, self.gT, m_dev=ned, aux=self.t[l])
+            self._lin(self.gT, k[f"b{l}.f0_w{sfx}"], None, self.g_rbf, m_dev=ned)
+            L.call("fmd_rbf_bwd", L.ptr(self.dist), L.ptr(self.g_rbf), None, self.cap, L.ptr(ned), L.ptr(w.centers),
+                   w.num_rbf, w.gamma, w.cutoff, L.ptr(self.g_d), 1, st)
+            self._n += 1
+            # g_h <- g_h + g_a @ lin1_w[f,h]
+            self._lin(self.g_a, k[f"b{l}.lin1_w"], None, gh_nxt, res=gh_cur)
+            gh_cur, gh_nxt = gh_nxt, gh_cur
+        L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(self.seg_ptr), L.ptr(self.dst), L.ptr(self.rev),
+               L.ptr(self.dist), L.ptr(self.g_d), self.N, self.cap, 1.0, L.ptr(self.forces), 0, st)
+        self._n += 1
+
+    # -- public ----------------------------------------------------------------------------------
+    def compute(self, pos: torch.Tensor):
+        """Fill self.energy [B] and self.forces [N,3] for `pos` [N,3] (fp32, CUDA, contiguous)."""
+        assert pos.is_cuda and pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape == (self.N, 3)
+        self._st = L.stream_ptr()
+        self._n = 0
+        if self.w is not None:
+            self._schnet(pos)
+            self.energy.copy_(self.e_schnet)
+        else:
+            self.energy.zero_()
+            self.forces.zero_()
+        self._n += 2
+        for p in self.priors:
+            L.call("fmd_prior_energy_forces", p.kind, L.ptr(pos), L.ptr(p.mapping), L.ptr(p.mapping_batch), p.n_terms,
+                   L.ptr(p.p0), L.ptr(p.p1), L.ptr(p.p2), p.n_degs, L.ptr(self.energy), L.ptr(self.forces), self._st)
+            self._n += 1
+        self.launches_per_eval = self._n
+        return self.energy, self.forces
+
+
+# ------------------------------------------------------------------------------------------------
+# Langevin engine
+# ------------------------------------------------------------------------------------------------
+
+
+class LangevinEngine:
+    """BAOAB steps (reference simulation/langevin.py:101-179) over a ForceField, optionally replayed
+    as a CUDA graph.  State (pos, vel, forces) lives in fixed device buffers."""
+
+    def __init__(self, ff: ForceField, pos: torch.Tensor, vel: torch.Tensor, masses: torch.Tensor,
+                 beta: torch.Tensor, dt: float, friction: float, seed: int = 0, use_graph: bool = True):
+        self.ff = ff
+        dev = ff.device
+        self.pos = pos.detach().to(dev).float().contiguous().clone()
+        self.vel = vel.detach().to(dev).float().contiguous().clone()
+        masses = masses.detach().to(dev).float().contiguous()
+        self.masses = masses
+        self.inv_mass = (1.0 / masses).contiguous()
+        sizes = (ff.mol_ptr[1:] - ff.mol_ptr[:-1]).long()
+        beta_atom = beta.detach().to(dev).float().repeat_interleave(sizes)
+        self.beta = beta.detach().to(dev).float().contiguous()
+        # beta_mass_ratio (reference simulation/langevin.py:211-215)
+        self.noise_std = torch.sqrt(1.0 / beta_atom / masses).contiguous()
+        self.dt = float(dt)
+        self.vscale = float(np.exp(-dt * friction))                 # langevin.py:76
+        self.noisescale = float(np.sqrt(1 - self.vscale * self.vscale))   # langevin.py:77
+        self.seed = int(seed) & ((1 << 64) - 1)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.ke = torch.zeros(ff.B, dtype=torch.float32, device=dev)
+        self.use_graph = use_graph
+        self.graph = None
+        self.n_steps_done = 0
+        self.launches_per_step = 0
+        ff.compute(self.pos)   # initial forces (reference simulation/base.py:525-526)
+
+    def _step_body(self, noise=None):
+        ff, st = self.ff, L.stream_ptr()
+        L.call("fmd_baoab_pre", L.ptr(self.pos), L.ptr(self.vel), L.ptr(ff.forces), L.ptr(self.inv_mass),
+               L.ptr(self.noise_std), L.ptr(noise), self.seed, 0, L.ptr(self.step_dev), ff.N, self.dt, self.vscale,
+               self.noisescale, st)
+        L.call("fmd_increment_u64", L.ptr(self.step_dev), st)
+        ff.compute(self.pos)
+        L.call("fmd_baoab_post", L.ptr(self.vel), L.ptr(ff.forces), L.ptr(self.inv_mass), ff.N, self.dt,
+               L.ptr(ff.mol_ptr), ff.B, L.ptr(self.ke), st)
+        self.launches_per_step = ff.launches_per_eval + 4
+
+    def step(self, noise: Optional[torch.Tensor] = None):
+        """One BAOAB step.  `noise` [N,3] replaces the Philox stream (step-exact parity tests)."""
+        if noise is not None or not self.use_graph:
+            self._step_body(noise)
+        else:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        self.n_steps_done += 1
+
+    def _capture(self):
+        # warm-up on a side stream (allocations, lazy module loads), then capture one step
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        saved = (self.pos.clone(), self.vel.clone(), self.ff.forces.clone(), self.step_dev.clone())
+        with torch.cuda.stream(s):
+            self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_body()
+        torch.cuda.synchronize()
+        # restore the state from before warm-up + capture-time execution (capture does not execute)
+        self.pos.copy_(saved[0]); self.vel.copy_(saved[1]); self.ff.forces.copy_(saved[2]); self.step_dev.copy_(saved[3])
+        self.graph = g
+
+    def run(self, n_steps: int):
+        for _ in range(n_steps):
+            self.step()
+
+    def kinetic_energy(self):
+        return self.ke
+
+    def temperature_kT(self):
+        """<2 KE / (3 n)> per molecule in energy units (equipartition: kT = 2 KE / dof)."""
+        sizes = (self.ff.mol_ptr[1:] - self.ff.mol_ptr[:-1]).float()
+        return 2.0 * self.ke / (3.0 * sizes)
+
+
+# ------------------------------------------------------------------------------------------------
+# builders for synthetic systems (benchmarks / tests)
+# ------------------------------------------------------------------------------------------------
+
+
+def prior_terms_from_system(system: dict, n_mols: int, device) -> List[PriorTerm]:
+    """Collated, condensed prior tables (what reference simulation/specialize_prior.py:112-207 plus
+    collate produce) for `n_mols` copies of the synthetic molecule of `flashmd.synthetic`."""
+    ty = system["atom_types"]
+    n = ty.shape[0]
+    st = system["stats"]
+    out = []
+
+    def collate(m):
+        nt = m.shape[1]
+        mp = np.concatenate([m + b * n for b in range(n_mols)], axis=1).astype(np.int32)
+        mb = np.repeat(np.arange(n_mols, dtype=np.int32), nt)
+        return torch.from_numpy(mp).to(device).contiguous(), torch.from_numpy(mb).to(device).contiguous()
+
+    def rep(v):
+        return torch.from_numpy(np.concatenate([np.asarray(v, dtype=np.float32)] * n_mols, 0)).to(device).contiguous()
+
+    m = system["bonds"]
+    tt = (ty[m[0]], ty[m[1]])
+    mp, mb = collate(m)
+    out.append(PriorTerm(L.PRIOR_BONDS, mp, mb, rep(st["bonds"]["k"][tt]), rep(st["bonds"]["x_0"][tt])))
+    m = system["angles"]
+    tt = (ty[m[0]], ty[m[1]], ty[m[2]])
+    mp, mb = collate(m)
+    out.append(PriorTerm(L.PRIOR_ANGLES, mp, mb, rep(st["angles"]["k"][tt]), rep(st["angles"]["x_0"][tt])))
+    m = system["dihedrals"]
+    c = (ty[m[1]], ty[m[2]])
+    nd = st["dihedrals"]["n_degs"]
+    k1 = np.stack([st["dihedrals"]["k1_central"][d][c] for d in range(nd)], 1)
+    k2 = np.stack([st["dihedrals"]["k2_central"][d][c] for d in range(nd)], 1)
+    mp, mb = collate(m)
+    out.append(PriorTerm(L.PRIOR_DIHEDRALS, mp, mb, rep(k1), rep(k2), rep(st["dihedrals"]["v0_central"][c]), nd))
+    m = system["nonbonded"]
+    tt = (ty[m[0]], ty[m[1]])
+    mp, mb = collate(m)
+    out.append(PriorTerm(L.PRIOR_REPULSION, mp, mb, rep(st["repulsion"]["sigma"][tt])))
+    return out
+
+
+def random_schnet_tensors(seed: int, num_rbf: int = 50, hidden: int = 128, filters: int = 128, num_blocks: int = 3,
+                          out_widths=(128, 64), embedding_size: int = 25) -> Dict[str, torch.Tensor]:
+    """Random-init CGSchNet weights with the reference's initialisation (Xavier-uniform weights,
+    zero biases: models/_module_init.py:4-28; N(0,1) embedding: torch.nn.Embedding default)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def xavier(o, i):
+        a = math.sqrt(6.0 / (i + o))
+        return (torch.rand((o, i), generator=g) * 2 - 1) * a
+
+    t = {"embedding": torch.randn((embedding_size, hidden), generator=g)}
+    for l in range(num_blocks):
+        t[f"b{l}.lin1_w"] = xavier(filters, hidden)
+        t[f"b{l}.f0_w"] = xavier(filters, num_rbf)
+        t[f"b{l}.f0_b"] = torch.zeros(filters)
+        t[f"b{l}.f1_w"] = xavier(filters, filters)
+        t[f"b{l}.lin2_w"] = xavier(hidden, filters)
+        t[f"b{l}.lin2_b"] = torch.zeros(hidden)
+        t[f"b{l}.lin_w"] = xavier(hidden, hidden)
+        t[f"b{l}.lin_b"] = torch.zeros(hidden)
+    widths = [hidden] + list(out_widths) + [1]
+    for i in range(len(widths) - 1):
+        t[f"out{i}_w"] = xavier(widths[i + 1], widths[i])
+        if i < len(widths) - 2:
+            t[f"out{i}_b"] = torch.zeros(widths[i + 1])
+    return t

@@ -1,0 +1,219 @@
+/*
+ * fmd_b200.h — C ABI of libfmd_b200.so: hand-written sm_100a kernels for the CGSchNet
+ * force-field + Langevin step (the hot path of UNITES-Lab/flash-molecular-dynamics).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers to DEVICE memory + sizes; no C++/torch types cross the boundary;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never allocates or
+ *     frees device memory and keeps no mutable global state besides the last error string;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the stream or the device;
+ *   - return 0 (FMD_OK) or a negative code; fmd_last_error() gives the text;
+ *   - `idx_bytes` selects the integer width of index arrays: 8 (int64, the reference's dtype)
+ *     or 4 (int32, used by the fused step);
+ *   - `wdt` / `xdt` / `ydt` select element types: FMD_F32 or FMD_F16;
+ *   - edge counts may live on the device: `n_edges_dev` (int32*, nullable) overrides the host
+ *     value `n_edges` (then `n_edges` is the buffer capacity) so a whole MD step can be captured
+ *     in a CUDA graph with no host round trip.
+ *
+ * "replaces:" cites the reference interface (paths under /root/reference/src/flashmd/).
+ */
+#ifndef FMD_B200_H
+#define FMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMD_OK 0
+#define FMD_ERR_INVALID (-1)
+#define FMD_ERR_CUDA (-2)
+#define FMD_ERR_UNSUPPORTED (-3)
+
+#define FMD_F32 0
+#define FMD_F16 1
+
+/* epilogue / prologue flags of fmd_linear */
+#define FMD_ACT_NONE 0
+#define FMD_ACT_TANH 1          /* tanhf */
+#define FMD_ACT_TANH_CLAMPED 2  /* (e^{2x}-1)/(e^{2x}+1), x clamped to +-10: kernels/cfconv_kernels.py:449-454 */
+
+const char* fmd_last_error(void);
+int fmd_version(void);
+/* number of SMs of the current device (148 on B200) */
+int fmd_sm_count(void);
+
+/* ---------------------------------------------------------------- neighbour list + CSR ----- */
+
+/* replaces: torch_cluster.radius_graph(x, r, batch, loop=False, max_num_neighbors,
+ * flow="target_to_source") as called by neighbor_list/torch_impl.py:216-224, fused with
+ * build_csr_index / build_src_csr_index (kernels/csr_kernels.py:88-169, 229-294).
+ * mol_ptr [n_mols+1] int32: first node of each molecule (nodes of a molecule are contiguous).
+ * Step 1: per-centre neighbour counts, deg [n_nodes] int32 (self excluded; at most
+ * max_num_neighbors+1 hits incl. self are considered, in ascending neighbour index).
+ * max_mol_size = largest mol_ptr[b+1]-mol_ptr[b] (host-known; sizes the grid). */
+int fmd_nl_count(const float* pos, const int32_t* mol_ptr, int n_mols, int n_nodes, int max_mol_size,
+                 float rc, int max_num_neighbors, int32_t* deg, void* stream);
+
+/* exclusive prefix sum: out[0..n] (n+1 values, out[n] = total). workspace: >= 4*(n/1024+2) bytes. */
+int fmd_exclusive_scan_i32(const int32_t* in, int32_t* out, int n, void* workspace, void* stream);
+
+/* Step 2: emit the edge list, centre-major ("src" ascending), neighbour ascending inside a
+ * centre — exactly radius_graph's order — plus the edge length ||pos[dst]-pos[src]||.
+ * seg_ptr [n_nodes+1] int32 = exclusive scan of deg (== src_ptr; for a symmetric list also dst_ptr).
+ * Edges beyond `capacity` are dropped (seg_ptr[n_nodes] still holds the true count).
+ * edge_src/edge_dst: idx_bytes wide. dist may be NULL. */
+int fmd_nl_fill(const float* pos, const int32_t* mol_ptr, int n_mols, int n_nodes, int max_mol_size,
+                float rc, int max_num_neighbors, const int32_t* seg_ptr, int capacity, void* edge_src,
+                void* edge_dst, int idx_bytes, float* dist, void* stream);
+
+/* Step 3: rev[e] = index of the edge (dst_e -> src_e) (binary search in dst_e's sorted segment),
+ * -1 if absent. For radius_graph output this IS csr_perm of build_csr_index(edge_dst) (stable
+ * order) and dst_ptr == seg_ptr. rev: idx_bytes wide. */
+int fmd_nl_reverse(const int32_t* seg_ptr, const void* edge_src, const void* edge_dst, int idx_bytes,
+                   int n_nodes, int capacity, void* rev, void* stream);
+
+/* replaces: build_csr_index(edge_dst, num_nodes) / build_src_csr_index(edge_src, num_nodes)
+ * (kernels/csr_kernels.py:88, :229) for ARBITRARY key arrays. ptr [num_nodes+1], perm [n_edges],
+ * both idx_bytes wide; perm is the STABLE counting-sort permutation (deterministic, unlike the
+ * reference's atomic-cursor fill). workspace: >= 4*(3*num_nodes + n_edges + num_nodes/1024 + 16) bytes. */
+int fmd_build_csr(const void* keys, int idx_bytes, int n_edges, int num_nodes, void* ptr, void* perm,
+                  void* workspace, void* stream);
+
+/* ---------------------------------------------------------------- edge features ------------- */
+
+/* replaces: fused_distance_gaussian_rbf_cutoff (kernels/cfconv_kernels.py:1470-1677), forward.
+ * dist [E] f32, rbf [E,R] f32 = exp(gamma (d-mu_k)^2) * 0.5(cos(pi d/rc)+1) [d<rc]. */
+int fmd_dist_rbf_cutoff_fwd(const float* pos, const void* edge_src, const void* edge_dst, int idx_bytes,
+                            int n_edges, const int32_t* n_edges_dev, const float* centers, int num_rbf,
+                            float gamma, float rc, float* dist, float* rbf, void* stream);
+
+/* replaces: FusedDistanceGaussianRBFCutoffFunction.backward (kernels/cfconv_kernels.py:1679-1735),
+ * first half: g_d[e] (+)= grad_dist[e] + sum_k grad_rbf[e,k] * d rbf_k / d d.
+ * grad_dist may be NULL. accumulate != 0 adds into g_d. */
+int fmd_rbf_bwd(const float* dist, const float* grad_rbf, const float* grad_dist, int n_edges,
+                const int32_t* n_edges_dev, const float* centers, int num_rbf, float gamma, float rc,
+                float* g_d, int accumulate, void* stream);
+
+/* second half, generic edge lists (atomic adds, like the reference's index_add_):
+ * grad_pos[dst] += g_d * u, grad_pos[src] -= g_d * u, u = (pos[dst]-pos[src]) / max(d, 1e-8).
+ * grad_pos [n_nodes,3] must be zero-initialised by the caller. */
+int fmd_edge_grad_to_pos_atomic(const float* pos, const void* edge_src, const void* edge_dst, int idx_bytes,
+                                const float* dist, const float* g_d, int n_edges,
+                                const int32_t* n_edges_dev, float* grad_pos, void* stream);
+
+/* second half, deterministic/atomic-free for the sorted symmetric list of fmd_nl_fill:
+ * out[i] = sign * sum_{e in seg(i)} (g_d[e] + g_d[rev[e]]) * u_e    (sign=+1 gives FORCES -dE/dx).
+ * accumulate != 0 adds into out. int32 indices. */
+int fmd_edge_grad_to_forces_csr(const float* pos, const int32_t* seg_ptr, const int32_t* edge_dst,
+                                const int32_t* rev, const float* dist, const float* g_d, int n_nodes,
+                                int n_edges, float sign, float* out, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- CFConv -------------------- */
+
+/* replaces: fused_csr_cfconv (kernels/csr_kernels.py:625-810) and fused_src_csr_grad_x (:302-482).
+ * out[i,:] = sum_{p in [seg_ptr[i], seg_ptr[i+1])} x[gather[e],:] * filt[e,:] * C(dist[e]),
+ *            e = perm ? perm[p] : p.
+ * forward of the reference: gather=edge_src, seg_ptr=dst_ptr, perm=csr_perm;
+ * grad_x of the reference:  gather=edge_dst, seg_ptr=src_ptr, perm=src_perm, x=grad_out;
+ * fused step (sorted symmetric list): gather=edge_dst, seg_ptr, perm=NULL for both directions.
+ * x [n_rows_x,F] f32, filt [E,F] wdt, out [n_nodes,F] f32. F % 4 == 0. Warp per destination,
+ * deterministic, atomic-free. seg_ptr/gather/perm are idx_bytes wide. Segment bounds are clamped to
+ * n_edges (the number of rows of filt / capacity of the edge buffers). */
+int fmd_cfconv_csr(const float* x, const void* filt, int wdt, const float* dist, const void* gather,
+                   const void* seg_ptr, const void* perm, int idx_bytes, int n_nodes, int n_edges, int n_feat,
+                   float rc, float* out, void* stream);
+
+/* replaces: fused_grad_filter_out (kernels/cfconv_kernels.py:178-337), plus the exact
+ * d(cutoff)/d(distance) term the reference's Triton backward drops (csr_kernels.py:912).
+ * g_filt[e,:] = x[src_e,:] * g_out[dst_e,:] * C(d_e)          (ydt = FMD_F32 | FMD_F16)
+ * g_dcut[e]  (+)= C'(d_e) * sum_f x[src_e,f] * g_out[dst_e,f] * filt[e,f]   (if g_dcut && filt) */
+int fmd_cfconv_grad_filter(const float* x, const float* g_out, const float* dist, const void* edge_src,
+                           const void* edge_dst, int idx_bytes, int n_edges, const int32_t* n_edges_dev,
+                           int n_feat, float rc, void* g_filt, int ydt, const void* filt, int wdt,
+                           float* g_dcut, int accumulate_dcut, void* stream);
+
+/* ---------------------------------------------------------------- dense layers -------------- */
+
+/* replaces: fused_tanh_linear (kernels/cfconv_kernels.py:1758-1941), fused_linear_tanh_fp16 (:644-760),
+ * linear_fp16 / linear_fp16_to_fp16 (:766-952), their backward GEMMs (:963-1226) and nn.Linear.
+ *   Y[M,N] = epi( pro(X)[M,K] @ W[K,N] + bias[N] ),  then optionally  Y *= (1 - aux^2),  Y += res
+ * X: xdt, W: wdt (row-major [K,N], i.e. nn.Linear.weight.t()), bias: wdt or NULL, Y: ydt,
+ * aux [M,N] (auxdt) or NULL (tanh-backward fusion), res [M,N] f32 or NULL (residual add).
+ * pro_act: FMD_ACT_* applied to X before the product; x_round_f16 != 0 rounds X to fp16 first
+ * (the reference's in-kernel cast, cfconv_kernels.py:701). fp32 accumulation, true fp32 FMA
+ * (no TF32). m_dev (int32*, nullable) overrides M (then M = capacity). */
+int fmd_linear(const void* X, int xdt, const void* W, int wdt, const void* bias, void* Y, int ydt, int M,
+               int N, int K, const int32_t* m_dev, int pro_act, int x_round_f16, int epi_act,
+               const void* aux, int auxdt, const float* res, void* stream);
+
+/* ---------------------------------------------------------------- node-level helpers -------- */
+
+/* replaces: torch.nn.Embedding (models/schnet.py:203). out[i,:] = table[types[i],:]. types: idx_bytes. */
+int fmd_embedding(const float* table, const void* types, int idx_bytes, int n_nodes, int n_feat, float* out,
+                  void* stream);
+
+/* replaces: scatter(energy, batch, reduce="sum") (models/schnet.py:355-357) for sorted `batch`:
+ * out[b] (+)= sum_{i in [mol_ptr[b], mol_ptr[b+1])} e_atom[i]; deterministic block reduction. */
+int fmd_segment_sum(const float* e_atom, const int32_t* mol_ptr, int n_mols, float* out, int accumulate,
+                    void* stream);
+
+/* ---------------------------------------------------------------- priors -------------------- */
+
+#define FMD_PRIOR_BONDS 0      /* k (d - x0)^2 + V0            prior/harmonic.py:122-123 + internal_coordinates.py:73-101 */
+#define FMD_PRIOR_ANGLES 1     /* k (cos(theta) - x0)^2 + V0   prior/harmonic.py:122-123 + internal_coordinates.py:140-170 */
+#define FMD_PRIOR_DIHEDRALS 2  /* v0 + sum_n k1_n sin(n phi) + k2_n cos(n phi)   prior/fourier_series.py:154-192 */
+#define FMD_PRIOR_REPULSION 3  /* (sigma / d)^6                 prior/repulsion.py:119-122 */
+
+/* replaces: prior.forward + its torch.autograd.grad (models/gradients.py:265) for one condensed
+ * prior term class. mapping [order, n_terms] int32 (row-major, rows = roles), mapping_batch
+ * [n_terms] int32, params: kind-specific flat f32 vectors
+ *   BONDS/ANGLES: p0=k[n_terms] p1=x0[n_terms] p2=V0[n_terms]|NULL
+ *   DIHEDRALS:    p0=k1[n_terms,n_degs] p1=k2[n_terms,n_degs] p2=v0[n_terms]
+ *   REPULSION:    p0=sigma[n_terms]
+ * energy [n_mols] and forces [n_nodes,3] are ACCUMULATED into (atomicAdd, like index_add_). */
+int fmd_prior_energy_forces(int kind, const float* pos, const int32_t* mapping, const int32_t* mapping_batch,
+                            int n_terms, const float* p0, const float* p1, const float* p2, int n_degs,
+                            float* energy, float* forces, void* stream);
+
+/* ---------------------------------------------------------------- integrator ---------------- */
+
+/* replaces: LangevinSimulation.timestep B-A-O-A (simulation/langevin.py:137-157).
+ * In place on pos/vel [n_nodes,3]. noise: external N(0,1) [n_nodes,3] or NULL -> counter-based
+ * Philox4x32-10 keyed by (seed), counter (step [+ *step_dev when non-NULL], node) + Box-Muller.
+ * inv_mass = 1/m [n_nodes]; noise_std = sqrt(1/(beta m)) [n_nodes] (beta_mass_ratio, :211-215). */
+int fmd_baoab_pre(float* pos, float* vel, const float* forces, const float* inv_mass, const float* noise_std,
+                  const float* noise, uint64_t seed, uint64_t step, const uint64_t* step_dev, int n_nodes,
+                  float dt, float vscale, float noisescale, void* stream);
+
+/* *counter += 1 on the stream (keeps the Philox step counter on the device so a captured CUDA
+ * graph of the whole step can be replayed; fmd_baoab_pre adds *step_dev to `step`). */
+int fmd_increment_u64(uint64_t* counter, void* stream);
+
+/* replaces: final B half-kick (simulation/langevin.py:169) (+ optional kinetic energy per molecule:
+ * ke[b] = 0.5 sum m v^2, langevin.py:266-270, when ke != NULL; mol_ptr then required). */
+int fmd_baoab_post(float* vel, const float* forces, const float* inv_mass, int n_nodes, float dt,
+                   const int32_t* mol_ptr, int n_mols, float* ke, void* stream);
+
+/* standard-normal stream used by fmd_baoab_pre when noise == NULL, exposed for tests. out [n_nodes,3]. */
+int fmd_philox_normal(uint64_t seed, uint64_t step, int n_nodes, float* out, void* stream);
+
+/* ---------------------------------------------------------------- replica exchange ---------- */
+
+/* replaces: PTSimulation._detect_exchange (simulation/parallel_tempering.py:368-413).
+ * accept[p] = u_p < exp((E[a_p]-E[b_p]) (beta[a_p]-beta[b_p])), u_p from `uniforms` or, when NULL,
+ * from Philox keyed by (seed, exchange_index, p) so every rank derives the same decisions. */
+int fmd_pt_decide(const float* energy, const float* beta, const int32_t* pair_a, const int32_t* pair_b,
+                  int n_pairs, const float* uniforms, uint64_t seed, uint64_t exchange_index, int32_t* accept,
+                  void* stream);
+
+/* replaces: PTSimulation._perform_exchange (:415-481) for pairs resident on this device:
+ * swap positions, swap velocities scaled by sqrt(beta_old/beta_new). n_atoms beads per sim. */
+int fmd_pt_swap(float* pos, float* vel, const float* beta, const int32_t* pair_a, const int32_t* pair_b,
+                const int32_t* accept, int n_pairs, int n_atoms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMD_B200_H */

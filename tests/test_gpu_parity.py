@@ -1,0 +1,372 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI / the drop-in `flashmd` package) against
+the CPU oracle and the golden vectors produced by the unmodified reference.  Run on the B200 box
+with `pytest -m gpu`.  Tolerances: integer/index work bit-exact; fp32 path 1e-5 relative L2 (the
+north-star bar); W16A16 path 1e-2 relative force error."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fmd_oracle as O
+from helpers import golden_params, golden_system, load_golden, prior_tables, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _engine_from_golden(g, precision="fp32", exact=True, priors=False, capacity=None):
+    from flashmd.engine import ForceField, PriorTerm, SchNetWeights
+    from flashmd import _lib as L
+    pos, types, batch, ptr, B, n = golden_system(g)
+    tensors = {k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w.")}
+    w = SchNetWeights.from_flat(tensors, float(g["sys.cutoff"]), int(g["meta.hparams"][2]), DEV)
+    pl = []
+    if priors:
+        kinds = {"bonds": L.PRIOR_BONDS, "angles": L.PRIOR_ANGLES, "dihedrals": L.PRIOR_DIHEDRALS,
+                 "repulsion": L.PRIOR_REPULSION}
+        for name, kind in kinds.items():
+            m, mb, p = prior_tables(g, name, B, n)
+            m, mb = m.to(torch.int32).to(DEV).contiguous(), mb.to(torch.int32).to(DEV).contiguous()
+            p = {k: v.to(DEV).contiguous() for k, v in p.items()}
+            if name in ("bonds", "angles"):
+                pl.append(PriorTerm(kind, m, mb, p["k"], p["x0"]))
+            elif name == "dihedrals":
+                pl.append(PriorTerm(kind, m, mb, p["k1s"], p["k2s"], p["v_0"], p["k1s"].shape[1]))
+            else:
+                pl.append(PriorTerm(kind, m, mb, p["sigma"]))
+    ff = ForceField(w, pl, types.to(DEV), torch.from_numpy(ptr).to(DEV), precision=precision,
+                    exact_cutoff_grad=exact, edge_capacity=capacity)
+    return ff, pos.to(DEV).contiguous()
+
+
+# ----------------------------------------------------------------------------- neighbour list / CSR
+def _random_molecules(seed, sizes, box):
+    rng = np.random.default_rng(seed)
+    pos = np.concatenate([rng.uniform(0, box, size=(s, 3)) for s in sizes]).astype(np.float32)
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return pos, ptr
+
+
+def _gpu_radius_graph(pos, ptr, rc, max_nn=1000, idx_dtype=torch.int32):
+    from flashmd.neighbor_list.torch_impl import radius_graph_csr
+    return radius_graph_csr(torch.from_numpy(pos).to(DEV), torch.from_numpy(ptr).to(DEV), rc, max_nn,
+                            idx_dtype=idx_dtype)
+
+
+@pytest.mark.parametrize("case", [
+    dict(seed=0, sizes=[54] * 4, box=14.0, rc=6.0),
+    dict(seed=1, sizes=[1, 2, 33, 7, 130, 64], box=10.0, rc=3.5),        # ragged, tiny molecules
+    dict(seed=2, sizes=[1200, 17], box=30.0, rc=5.0),                    # molecule larger than one smem tile
+    dict(seed=3, sizes=[40, 40], box=3.0, rc=50.0),                      # fully connected
+    dict(seed=4, sizes=[300], box=6.0, rc=50.0, max_nn=32),              # max_num_neighbors truncation
+    dict(seed=5, sizes=[5, 5], box=100.0, rc=0.01),                      # no edges at all
+])
+@pytest.mark.parametrize("idx_dtype", [torch.int32, torch.int64])
+def test_radius_graph_csr_bit_exact(case, idx_dtype):
+    pos, ptr = _random_molecules(case["seed"], case["sizes"], case["box"])
+    max_nn = case.get("max_nn", 1000)
+    ref = O.radius_graph(pos, ptr, case["rc"], max_nn)
+    out = _gpu_radius_graph(pos, ptr, case["rc"], max_nn, idx_dtype)
+    ei = out["edge_index"].cpu().numpy()
+    assert ei.dtype == (np.int32 if idx_dtype == torch.int32 else np.int64)
+    np.testing.assert_array_equal(ei.astype(np.int64), ref)
+    N = pos.shape[0]
+    sptr, _ = O.build_csr(ref[0], N)
+    np.testing.assert_array_equal(out["src_ptr"].cpu().numpy().astype(np.int64), sptr)
+    rev = O.reverse_edge_index(ref, N)
+    np.testing.assert_array_equal(out["rev"].cpu().numpy().astype(np.int64), rev)
+    d = np.linalg.norm(pos[ref[1]].astype(np.float64) - pos[ref[0]].astype(np.float64), axis=1)
+    np.testing.assert_allclose(out["dist"].cpu().numpy(), d, rtol=2e-6)
+    if max_nn >= max(case["sizes"]):
+        dptr, perm = O.build_csr(ref[1], N)           # symmetric: dst-major CSR == reverse map
+        np.testing.assert_array_equal(sptr, dptr)
+        np.testing.assert_array_equal(rev, perm)
+
+
+@pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz"])
+def test_radius_graph_golden(name):
+    g = load_golden(name)
+    pos, types, batch, ptr, B, n = golden_system(g)
+    out = _gpu_radius_graph(pos.numpy(), ptr.astype(np.int64), float(g["sys.cutoff"]))
+    np.testing.assert_array_equal(out["edge_index"].cpu().numpy().astype(np.int64), g["ref.schnet_edge_index"])
+
+
+@pytest.mark.parametrize("E,N", [(0, 5), (1, 1), (1000, 17), (200000, 5000), (70000, 3)])
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+def test_build_csr_index_generic(E, N, dtype):
+    from flashmd.kernels import build_csr_index, build_src_csr_index
+    rng = np.random.default_rng(E + N)
+    keys = rng.integers(0, N, size=E)
+    for fn in (build_csr_index, build_src_csr_index):
+        ptr, perm = fn(torch.from_numpy(keys).to(dtype).to(DEV), N)
+        rptr, rperm = O.build_csr(keys, N)
+        assert ptr.dtype == dtype and perm.dtype == dtype
+        np.testing.assert_array_equal(ptr.cpu().numpy().astype(np.int64), rptr)
+        np.testing.assert_array_equal(perm.cpu().numpy().astype(np.int64), rperm)
+
+
+# ----------------------------------------------------------------------------- operator-level kernels
+def test_fused_distance_rbf_cutoff_fwd_bwd():
+    from flashmd.kernels import fused_distance_gaussian_rbf_cutoff_autograd
+    g = load_golden("schnet_n54_b4.npz")
+    pos, types, batch, ptr, B, n = golden_system(g)
+    ei = torch.from_numpy(g["ref.schnet_edge_index"])
+    rc = float(g["sys.cutoff"])
+    centers, gamma = O.rbf_params(rc, 50)
+    p = pos.clone().requires_grad_(True)
+    d_ref = O.edge_distances(p, ei)
+    rbf_ref = O.gaussian_rbf(d_ref, centers, gamma, rc)
+    wr = torch.randn(rbf_ref.shape, generator=torch.Generator().manual_seed(0))
+    wd = torch.randn(d_ref.shape, generator=torch.Generator().manual_seed(1))
+    (g_ref,) = torch.autograd.grad((rbf_ref * wr).sum() + (d_ref * wd).sum(), p)
+    pc = pos.to(DEV).requires_grad_(True)
+    d, rbf = fused_distance_gaussian_rbf_cutoff_autograd(pc, ei[0].to(DEV).contiguous(), ei[1].to(DEV).contiguous(),
+                                                         centers.to(DEV), gamma, rc)
+    assert rel_l2(d.detach().cpu(), d_ref.detach()) < 1e-6
+    assert rel_l2(rbf.detach().cpu(), rbf_ref.detach()) < 1e-5
+    (g_gpu,) = torch.autograd.grad((rbf * wr.to(DEV)).sum() + (d * wd.to(DEV)).sum(), pc)
+    assert rel_l2(g_gpu.cpu(), g_ref) < 1e-5
+
+
+@pytest.mark.parametrize("fdt", [torch.float32, torch.float16])
+@pytest.mark.parametrize("F", [128, 64, 20])
+def test_cfconv_csr_and_grads(fdt, F):
+    from flashmd import kernels as K
+    g = load_golden("schnet_n54_b4.npz")
+    pos, types, batch, ptr, B, n = golden_system(g)
+    N = B * n
+    ei = torch.from_numpy(g["ref.schnet_edge_index"])
+    E = ei.shape[1]
+    rc = float(g["sys.cutoff"])
+    gen = torch.Generator().manual_seed(F)
+    x = torch.randn(N, F, generator=gen)
+    filt = torch.randn(E, F, generator=gen).to(fdt)
+    d = O.edge_distances(pos, ei)
+    go = torch.randn(N, F, generator=gen)
+    # oracle (PyTorch path of the reference: models/schnet.py:706-715)
+    xr, fr, dr = x.clone().requires_grad_(True), filt.float().clone().requires_grad_(True), d.clone().requires_grad_(True)
+    out_ref = torch.zeros(N, F).index_add(0, ei[1], xr[ei[0]] * fr * O.cosine_cutoff(dr, rc)[:, None])
+    gx_ref, gf_ref, gd_ref = torch.autograd.grad((out_ref * go).sum(), (xr, fr, dr))
+    src, dst = ei[0].to(DEV).contiguous(), ei[1].to(DEV).contiguous()
+    dst_ptr, csr_perm = K.build_csr_index(dst, N)
+    src_ptr, src_perm = K.build_src_csr_index(src, N)
+    xg, fg, dg = x.to(DEV).requires_grad_(True), filt.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+    out = K.fused_csr_cfconv_autograd(xg, fg, dg, src, dst, dst_ptr, csr_perm, N, rc, src_ptr, src_perm)
+    tol = 1e-5 if fdt == torch.float32 else 1e-5
+    assert rel_l2(out.detach().cpu(), out_ref.detach()) < tol
+    gx, gf, gd = torch.autograd.grad((out * go.to(DEV)).sum(), (xg, fg, dg))
+    assert rel_l2(gx.cpu(), gx_ref) < 1e-5
+    assert gf.dtype == fdt
+    assert rel_l2(gf.float().cpu(), gf_ref) < (1e-5 if fdt == torch.float32 else 1e-3)
+    assert rel_l2(gd.cpu(), gd_ref) < 1e-5
+    # atomic-named variant gives the same result deterministically
+    out2 = K.fused_cutoff_gather_multiply_scatter(x.to(DEV), filt.to(DEV), d.to(DEV), src, dst, N, rc)
+    assert torch.equal(out2, out.detach())
+    # empty edge list -> zeros (reference csr_kernels.py:782-784)
+    z = K.fused_csr_cfconv(x.to(DEV), filt[:0].to(DEV), d[:0].to(DEV), src[:0], torch.zeros(N + 1, dtype=torch.int64, device=DEV),
+                           src[:0], N, rc)
+    assert z.shape == (N, F) and float(z.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 50, 128), (777, 128, 128), (300, 128, 64), (129, 64, 1), (5, 3, 7)])
+def test_dense_layers(M, K, N):
+    from flashmd import kernels as Kn
+    gen = torch.Generator().manual_seed(M)
+    x = torch.randn(M, K, generator=gen)
+    w = torch.randn(K, N, generator=gen) / K ** 0.5
+    b = torch.randn(N, generator=gen)
+    xg = x.to(DEV).requires_grad_(True)
+    y = Kn.fused_tanh_linear_autograd(xg, w.to(DEV), b.to(DEV))
+    xr = x.double().requires_grad_(True)
+    yr = torch.tanh(xr) @ w.double() + b.double()
+    assert rel_l2(y.detach().cpu(), yr.detach()) < 2e-6
+    go = torch.randn(M, N, generator=gen)
+    (gx,) = torch.autograd.grad((y * go.to(DEV)).sum(), xg)
+    (gxr,) = torch.autograd.grad((yr * go.double()).sum(), xr)
+    assert rel_l2(gx.cpu(), gxr) < 2e-6
+    # fp16 layers (W16A16): fp16-rounded operands, fp32 accumulate, clamped tanh, fp16 store
+    w16, b16 = w.half(), b.half()
+    y16 = Kn.fused_linear_tanh_fp16(x.to(DEV), w16.to(DEV), b16.to(DEV))
+    ref = O._tanh_w16(x.half().double() @ w16.double() + b16.double()).half()
+    assert y16.dtype == torch.float16
+    assert rel_l2(y16.float().cpu(), ref.float()) < 1e-3
+    y32 = Kn.linear_fp16(x.half().to(DEV), w16.to(DEV))
+    assert y32.dtype == torch.float32
+    assert rel_l2(y32.cpu(), x.half().double() @ w16.double()) < 2e-6
+
+
+# ----------------------------------------------------------------------------- whole force field
+@pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz"])
+def test_schnet_fp32_vs_reference_golden(name):
+    """fp32 energies and forces within 1e-5 relative of the reference's fp32 path (north star)."""
+    g = load_golden(name)
+    ff, pos = _engine_from_golden(g, "fp32")
+    e, f = ff.compute(pos)
+    assert ff.num_edges() == g["ref.schnet_edge_index"].shape[1]
+    # the reference's own fp32 CPU result carries ~1e-6 rounding noise; fp64 reference is the tighter check
+    assert rel_l2(e.cpu(), g["ref64.energy.SchNet"]) < 1e-5
+    assert rel_l2(f.cpu(), g["ref64.forces.SchNet"]) < 1e-5
+    assert rel_l2(e.cpu(), g["ref32.energy.SchNet"]) < 1e-5
+    assert rel_l2(f.cpu(), g["ref32.forces.SchNet"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz"])
+def test_total_model_with_priors_vs_reference_golden(name):
+    g = load_golden(name)
+    ff, pos = _engine_from_golden(g, "fp32", priors=True)
+    e, f = ff.compute(pos)
+    assert rel_l2(e.cpu(), g["ref64.energy.total"]) < 1e-5
+    assert rel_l2(f.cpu(), g["ref64.forces.total"]) < 1e-5
+    # determinism of the SchNet part: two evaluations are bitwise identical
+    ff2, _ = _engine_from_golden(g, "fp32")
+    f1 = ff2.compute(pos)[1].clone()
+    f2 = ff2.compute(pos)[1].clone()
+    assert torch.equal(f1, f2)
+
+
+@pytest.mark.parametrize("kind", ["bonds", "angles", "dihedrals", "repulsion"])
+def test_prior_terms(kind):
+    from flashmd.engine import ForceField
+    g = load_golden("schnet_n54_b4.npz")
+    ff, pos = _engine_from_golden(g, "fp32", priors=True)
+    idx = ["bonds", "angles", "dihedrals", "repulsion"].index(kind)
+    ff1 = ForceField(None, [ff.priors[idx]], ff.types, ff.mol_ptr)
+    e, f = ff1.compute(pos)
+    assert rel_l2(e.cpu(), g[f"ref64.energy.{kind}"]) < 2e-6
+    assert rel_l2(f.cpu(), g[f"ref64.forces.{kind}"]) < 1e-5
+
+
+def test_schnet_triton_compat_mode_drops_cutoff_gradient():
+    """exact_cutoff_grad=False reproduces the reference Triton backward (csr_kernels.py:912)."""
+    g = load_golden("schnet_n54_b4.npz")
+    pos, types, batch, ptr, B, n = golden_system(g)
+    P = golden_params(g)
+    ei = torch.from_numpy(g["ref.schnet_edge_index"])
+    e_ref, f_ref = O.schnet_energy_forces(P, pos, types, batch, B, ei, drop_cutoff_grad=True)
+    ff, posg = _engine_from_golden(g, "fp32", exact=False)
+    e, f = ff.compute(posg)
+    assert rel_l2(f.cpu(), f_ref) < 1e-5
+    assert rel_l2(f.cpu(), g["ref64.forces.SchNet"]) > 1e-3   # and it really differs from the exact one
+
+
+@pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz"])
+def test_schnet_w16a16(name):
+    """W16A16 path within 1e-2 relative force error of the W16A16 rounding model (and of fp32)."""
+    g = load_golden(name)
+    pos, types, batch, ptr, B, n = golden_system(g)
+    P = golden_params(g)
+    ei = torch.from_numpy(g["ref.schnet_edge_index"])
+    e_ref, f_ref = O.schnet_energy_forces(P, pos, types, batch, B, ei, precision="w16a16")
+    ff, posg = _engine_from_golden(g, "w16a16")
+    e, f = ff.compute(posg)
+    assert rel_l2(f.cpu(), f_ref) < 1e-2
+    assert rel_l2(e.cpu(), e_ref) < 1e-2
+    assert rel_l2(f.cpu(), g["ref64.forces.SchNet"]) < 2e-2
+
+
+def test_edge_capacity_and_large_batch_properties():
+    """cfg2-shaped (B=128, n=269) run: size-independent properties — edge list symmetric and sorted,
+    forces sum to zero per molecule (translation invariance), identical molecules give identical
+    results, W16A16 close to fp32."""
+    from flashmd import synthetic
+    from flashmd.engine import ForceField, SchNetWeights, random_schnet_tensors
+    B, n = 128, 269
+    sysd = synthetic.synthetic_system(8, n, seed=0)
+    pos8 = torch.from_numpy(sysd["pos"])
+    pos = pos8.repeat(B // 8, 1, 1).reshape(B * n, 3).to(DEV).contiguous()
+    types = torch.from_numpy(sysd["atom_types"]).repeat(B).to(DEV)
+    ptr = (torch.arange(B + 1) * n).to(DEV)
+    w = SchNetWeights.from_flat(random_schnet_tensors(0), sysd["cutoff"], 50, DEV)
+    ff = ForceField(w, [], types, ptr, precision="fp32", edge_capacity=int(B * n * 70))
+    e, f = ff.compute(pos)
+    E = ff.num_edges()
+    assert 40 * B * n < E < 70 * B * n
+    src, dst, rev = ff.src[:E].long(), ff.dst[:E].long(), ff.rev[:E].long()
+    assert bool((src[1:] >= src[:-1]).all())
+    assert bool(((dst[1:] > dst[:-1]) | (src[1:] != src[:-1])).all())
+    assert bool((rev >= 0).all()) and bool((src[rev] == dst).all()) and bool((dst[rev] == src).all())
+    fm = f.view(B, n, 3)
+    assert float(fm.sum(1).abs().max()) < 2e-3 * float(fm.abs().max())
+    assert torch.equal(fm[:8], fm[8:16]) and torch.equal(e[:8], e[120:128])
+    ff16 = ForceField(w, [], types, ptr, precision="w16a16", edge_capacity=int(B * n * 70))
+    e16, f16 = ff16.compute(pos)
+    assert rel_l2(f16.cpu(), f.cpu()) < 1e-2
+    # oracle on the first molecule only (seconds on CPU)
+    P = O.SchNetParams({k: (v if v is None else v.clone()) for k, v in random_schnet_tensors(0).items()} |
+                       {"out2_b": None}, 3, 3, sysd["cutoff"], 50)
+    p0 = pos[:n].cpu()
+    ei = torch.from_numpy(O.radius_graph(p0.numpy(), np.array([0, n]), sysd["cutoff"]))
+    e0, f0 = O.schnet_energy_forces(P.to(torch.float64), p0.double(), types[:n].cpu(), torch.zeros(n, dtype=torch.long), 1, ei)
+    assert rel_l2(f[:n].cpu(), f0) < 1e-5 and rel_l2(e[:1].cpu(), e0) < 1e-5
+
+
+# ----------------------------------------------------------------------------- integrator
+def test_langevin_trajectory_vs_reference_golden():
+    """10 BAOAB steps replayed with the reference's own noise (simulation/langevin.py:101-179)."""
+    from flashmd.engine import LangevinEngine
+    g = load_golden("schnet_n54_b4.npz")
+    t = load_golden("langevin_n54_b4.npz")
+    ff, pos = _engine_from_golden(g, "fp32", priors=True)
+    B, n = 4, 54
+    dt, friction, beta, _ = t["params"]
+    masses = torch.from_numpy(g["sys.masses"]).repeat(B)
+    eng = LangevinEngine(ff, pos, torch.from_numpy(t["v0"]), masses, torch.full((B,), float(beta)), dt, friction,
+                         use_graph=False)
+    for s in range(t["noise"].shape[0]):
+        eng.step(noise=torch.from_numpy(t["noise"][s]).to(DEV).contiguous())
+        assert rel_l2(eng.pos.view(B, n, 3).cpu(), t["coords"][:, s]) < 1e-6
+        assert rel_l2(ff.forces.view(B, n, 3).cpu(), t["forces"][:, s]) < 5e-4
+        assert rel_l2(ff.energy.cpu(), t["potential"][:, s]) < 1e-5
+        assert rel_l2(eng.ke.cpu(), t["kinetic"][:, s]) < 1e-5
+
+
+def test_philox_noise_statistics_and_graph_replay():
+    from flashmd import _lib as L
+    from flashmd.engine import LangevinEngine
+    n = 1 << 18
+    out = torch.empty((n, 3), device=DEV)
+    L.call("fmd_philox_normal", 1234, 7, n, L.ptr(out), L.stream_ptr())
+    out2 = torch.empty((n, 3), device=DEV)
+    L.call("fmd_philox_normal", 1234, 7, n, L.ptr(out2), L.stream_ptr())
+    assert torch.equal(out, out2)                      # counter-based: reproducible
+    L.call("fmd_philox_normal", 1234, 8, n, L.ptr(out2), L.stream_ptr())
+    assert not torch.equal(out, out2)
+    x = out.double().cpu().numpy().ravel()
+    assert abs(x.mean()) < 5e-3 and abs(x.std() - 1) < 5e-3
+    assert abs((x ** 3).mean()) < 2e-2 and abs((x ** 4).mean() - 3) < 5e-2
+    assert abs(np.corrcoef(out[:, 0].cpu().numpy(), out[:, 1].cpu().numpy())[0, 1]) < 5e-3
+    # CUDA-graph replay == eager stepping (same Philox counters)
+    g = load_golden("schnet_n24_b3_l2.npz")
+    B, nn = 3, 24
+    masses = torch.from_numpy(g["sys.masses"]).repeat(B)
+    res = []
+    for use_graph in (False, True):
+        ff, pos = _engine_from_golden(g, "fp32", priors=True)
+        eng = LangevinEngine(ff, pos, torch.zeros(B * nn, 3), masses, torch.full((B,), 1.67), 0.004, 1.0, seed=11,
+                             use_graph=use_graph)
+        eng.run(20)
+        res.append((eng.pos.clone(), eng.vel.clone()))
+    assert rel_l2(res[1][0].cpu(), res[0][0].cpu()) < 1e-5
+    assert rel_l2(res[1][1].cpu(), res[0][1].cpu()) < 1e-3
+
+
+def test_pt_exchange_vs_reference_golden():
+    from flashmd import _lib as L
+    g = load_golden("pt_n24.npz")
+    betas = torch.from_numpy(g["beta_per_sim"].astype(np.float32)).to(DEV)
+    n = 24
+    for rnd, (a, b) in enumerate([(g["even_a"], g["even_b"]), (g["odd_a"], g["odd_b"])]):
+        pa = torch.from_numpy(a.astype(np.int32)).to(DEV)
+        pb = torch.from_numpy(b.astype(np.int32)).to(DEV)
+        e = torch.from_numpy(g[f"round{rnd}.energies"]).to(DEV)
+        u = torch.from_numpy(g[f"round{rnd}.uniforms"]).to(DEV)
+        acc = torch.zeros(len(a), dtype=torch.int32, device=DEV)
+        L.call("fmd_pt_decide", L.ptr(e), L.ptr(betas), L.ptr(pa), L.ptr(pb), len(a), L.ptr(u), 0, 0, L.ptr(acc),
+               L.stream_ptr())
+        ok = O.pt_exchange(g[f"round{rnd}.energies"], g["beta_per_sim"].astype(np.float32), a, b, g[f"round{rnd}.uniforms"])
+        np.testing.assert_array_equal(acc.cpu().numpy().astype(bool), ok)
+        x = torch.from_numpy(g[f"round{rnd}.x_before"]).to(DEV).contiguous()
+        v = torch.from_numpy(g[f"round{rnd}.v_before"]).to(DEV).contiguous()
+        L.call("fmd_pt_swap", L.ptr(x), L.ptr(v), L.ptr(betas), L.ptr(pa), L.ptr(pb), L.ptr(acc), len(a), n,
+               L.stream_ptr())
+        np.testing.assert_array_equal(x.cpu().numpy(), g[f"round{rnd}.x_after"])
+        np.testing.assert_allclose(v.cpu().numpy(), g[f"round{rnd}.v_after"], rtol=1e-6, atol=1e-7)
