@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the CGSchNet force-field + Langevin step (BASELINE.json metric: timestep·mol/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--precision w16a16|fp32] [--n-beads 269] [--batch 128]
+
+One "step" = one BAOAB Langevin step (neighbour list -> SchNet energy -> analytic forces ->
+priors -> integrator) of `batch` molecules per GPU.  N>1 (under torchrun): every rank runs its own
+independent replica batch (no data-path collective; weak scaling), time = max over ranks.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "flash-molecular-dynamics_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "timestep*mol/s, CGSchNet 1ENH batch128 Langevin"
+UNIT = "timestep*mol/s"
+DT, FRICTION, BETA, SEED = 0.004, 1.0, 1.67, 103838     # reference examples/langevin.yaml:2-9
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="w16a16", choices=["w16a16", "fp32"])
+    ap.add_argument("--n-beads", type=int, default=269)
+    ap.add_argument("--batch", type=int, default=128, help="molecules per GPU")
+    ap.add_argument("--blocks", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="print per-kernel event timings to stderr")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_system(args, seed):
+    from flashmd import synthetic
+    n_distinct = min(args.batch, 16)
+    sysd = synthetic.synthetic_system(n_distinct, args.n_beads, seed=seed)
+    reps = -(-args.batch // n_distinct)
+    pos = np.concatenate([sysd["pos"]] * reps, 0)[: args.batch]
+    return sysd, pos
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+
+
+def cpu_oracle_throughput(args, n_mols, n_steps, threads):
+    """BAOAB steps of `n_mols` molecules with the CPU oracle (fp32 PyTorch path = the reference's
+    --disable_optim semantics).  Returns (timestep*mol/s, seconds)."""
+    from oracle import fmd_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.set_num_threads(threads)
+    from flashmd import synthetic
+    from flashmd.engine import random_schnet_tensors
+    sysd = synthetic.synthetic_system(n_mols, args.n_beads, seed=0)
+    n = args.n_beads
+    pos = torch.from_numpy(sysd["pos"]).reshape(n_mols * n, 3)
+    types = torch.from_numpy(sysd["atom_types"]).repeat(n_mols)
+    batch = torch.arange(n_mols).repeat_interleave(n)
+    ptr = np.arange(n_mols + 1) * n
+    t = random_schnet_tensors(0, num_blocks=args.blocks)
+    t.setdefault("out2_b", None)
+    P = O.SchNetParams(t, args.blocks, 3, sysd["cutoff"], 50)
+    masses = torch.from_numpy(sysd["masses"]).repeat(n_mols)
+    bmr = torch.sqrt(1.0 / (BETA * masses))[:, None]
+    vs, ns = O.baoab_constants(DT, FRICTION)
+    pri = _oracle_priors(sysd, n_mols)
+
+    def force(x):
+        ei = torch.from_numpy(O.radius_graph(x.numpy(), ptr, sysd["cutoff"]))
+        e, f = O.schnet_energy_forces(P, x, types, batch, n_mols, ei)
+        for kind, (m, mb, pr) in pri.items():
+            ek, fk = O.prior_energy_forces(kind, x, m, mb, n_mols, pr)
+            e, f = e + ek, f + fk
+        return e, f
+
+    x, v = pos, torch.zeros_like(pos)
+    _, f = force(x)
+    g = torch.Generator().manual_seed(SEED)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        noise = torch.empty_like(x).normal_(generator=g)
+        x, v = O.baoab_pre(x, v, f, masses, bmr, noise, DT, vs, ns)
+        x, v = x.float(), v.float()
+        e, f = force(x)
+        v = O.baoab_post(v, f, masses, DT).float()
+    dtm = time.perf_counter() - t0
+    return n_mols * n_steps / dtm, dtm
+
+
+def _oracle_priors(sysd, B):
+    ty, st, n = sysd["atom_types"], sysd["stats"], sysd["atom_types"].shape[0]
+    out = {}
+
+    def col(m):
+        return (torch.from_numpy(np.concatenate([m + b * n for b in range(B)], 1)),
+                torch.from_numpy(np.repeat(np.arange(B), m.shape[1])))
+
+    def rep(v):
+        return torch.from_numpy(np.concatenate([np.asarray(v, np.float32)] * B, 0))
+    m = sysd["bonds"]; tt = (ty[m[0]], ty[m[1]])
+    out["bonds"] = (*col(m), {"k": rep(st["bonds"]["k"][tt]), "x0": rep(st["bonds"]["x_0"][tt])})
+    m = sysd["angles"]; tt = (ty[m[0]], ty[m[1]], ty[m[2]])
+    out["angles"] = (*col(m), {"k": rep(st["angles"]["k"][tt]), "x0": rep(st["angles"]["x_0"][tt])})
+    m = sysd["dihedrals"]; c = (ty[m[1]], ty[m[2]]); nd = st["dihedrals"]["n_degs"]
+    out["dihedrals"] = (*col(m), {
+        "k1s": rep(np.stack([st["dihedrals"]["k1_central"][d][c] for d in range(nd)], 1)),
+        "k2s": rep(np.stack([st["dihedrals"]["k2_central"][d][c] for d in range(nd)], 1)),
+        "v_0": rep(st["dihedrals"]["v0_central"][c])})
+    m = sysd["nonbonded"]; tt = (ty[m[0]], ty[m[1]])
+    out["repulsion"] = (*col(m), {"sigma": rep(st["repulsion"]["sigma"][tt])})
+    return out
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_mols, per_step = 4, 1
+    steps, warm = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    if warm:
+        cpu_oracle_throughput(args, n_mols, warm, cores)
+    val, secs = cpu_oracle_throughput(args, n_mols, steps * per_step, cores)
+    sample = (f"{n_mols} molecules x {args.n_beads} beads, {steps} BAOAB steps, oracle port of the reference's "
+              f"--disable_optim fp32 PyTorch path (oracle/fmd_oracle.py), {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": f"CGSchNet 1ENH-shaped synthetic CG protein, {args.n_beads} beads/molecule, batch "
+                        f"{args.batch} per GPU, {args.blocks} interaction blocks, F=128, R=50, Langevin beta={BETA} "
+                        f"dt={DT}; priors: bonds+angles+dihedrals+repulsion",
+            "n_beads": args.n_beads, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+            "precision_path": args.precision, "parallelism": f"replica-sharded x{world} (no data-path collective)",
+            "l2": "per-step working set (edge tensors, >1 GB) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from flashmd import _lib as L
+    from flashmd.engine import (ForceField, LangevinEngine, SchNetWeights, prior_terms_from_system,
+                                random_schnet_tensors)
+    L.load()
+    sysd, pos_np = build_system(args, seed=rank)
+    B, n = args.batch, args.n_beads
+    pos = torch.from_numpy(pos_np).reshape(B * n, 3).to(dev).contiguous()
+    types = torch.from_numpy(sysd["atom_types"]).repeat(B).to(dev)
+    mol_ptr = (torch.arange(B + 1) * n).to(dev)
+    w = SchNetWeights.from_flat(random_schnet_tensors(0, num_blocks=args.blocks), sysd["cutoff"], 50, dev)
+    priors = prior_terms_from_system(sysd, B, dev)
+    # edge capacity: 1.35x the initial edge count (density stays bounded by the repulsion/bond priors)
+    from flashmd.neighbor_list import radius_graph_csr
+    e0 = radius_graph_csr(pos, mol_ptr, sysd["cutoff"], idx_dtype=torch.int32)["edge_index"].shape[1]
+    cap = int(1.35 * e0) + 4096
+    ff = ForceField(w, priors, types, mol_ptr, precision=args.precision, edge_capacity=cap)
+    masses = torch.from_numpy(sysd["masses"]).repeat(B)
+    g = torch.Generator().manual_seed(1234 + rank)
+    v0 = torch.randn((B * n, 3), generator=g) * torch.sqrt(1.0 / (BETA * masses))[:, None]
+    eng = LangevinEngine(ff, pos, v0, masses, torch.full((B,), BETA), DT, FRICTION, seed=SEED + rank, use_graph=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(max(args.warmup, 3)):
+        eng.step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    edges_now = ff.num_edges()
+    assert edges_now <= cap, f"edge capacity overflow: {edges_now} > {cap}"
+    assert torch.isfinite(eng.pos).all(), "trajectory diverged"
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (H2D + step + D2H inside the timed region)
+    ph = torch.empty((B * n, 3), dtype=torch.float32).pin_memory()
+    vh = torch.empty((B * n, 3), dtype=torch.float32).pin_memory()
+    fh = torch.empty((B * n, 3), dtype=torch.float32).pin_memory()
+    eh = torch.empty(B, dtype=torch.float32).pin_memory()
+    ph.copy_(eng.pos); vh.copy_(eng.vel); fh.copy_(ff.forces)
+    for _ in range(3):
+        eng.step_host(ph, vh, fh, eh)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.step_host(ph, vh, fh, eh)
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = 3 * B * n * 3 * 4
+    d2h = 3 * B * n * 3 * 4 + B * 4
+
+    # ---- roofline of the dominant kernel (CFConv CSR segment reduce), CUDA events on the launch stream
+    roof, kern_table = kernel_roofline(ff, eng, args, edges_now)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 filter tensors / f32 accumulate" if args.precision == "w16a16" else "f32",
+            "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": eng.launches_per_step * args.steps,
+            "launches_per_step": eng.launches_per_step,
+            "edges": edges_now, "nodes": B * n,
+            "roofline": roof, "kernels_ms_per_step": kern_table,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            nm = 2
+            val, secs = cpu_oracle_throughput(args, nm, 2, cores)
+            line["cpu_baseline"] = {
+                "value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{nm} molecules x {n} beads, 2 BAOAB steps ({secs:.1f} s), oracle port of the reference's "
+                          f"--disable_optim fp32 PyTorch path, {cores} threads"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(ff, eng, args, E):
+    """Per-kernel-class device time of one eager step (CUDA events on the launching stream, 3 reps),
+    and the roofline entry of the dominant kernel.  Algorithmic bytes per launch:
+    CFConv CSR: E*F*b (filter) + 4*N*F (x, once) + 4*N*F (out) + 4*E (dst idx) + 4*E (dist) + 4*(N+1)."""
+    from flashmd import _lib as L
+    peak, which = peaks()
+    N, F = ff.N, ff.w.filters
+    b = 2 if args.precision == "w16a16" else 4
+    timings = {}
+    lib = L.load()
+    orig_call = L.call
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        timings.setdefault(name, []).append((e0, e1))
+
+    import flashmd.engine as E_mod
+    reps = 3
+    E_mod.L.call = timed_call
+    try:
+        for _ in range(reps):
+            eng._step_body()
+        torch.cuda.synchronize()
+    finally:
+        E_mod.L.call = orig_call
+    table = {}
+    for name, evs in timings.items():
+        tot = sum(a.elapsed_time(bb) for a, bb in evs)
+        table[name] = {"ms_per_step": tot / reps, "launches_per_step": len(evs) // reps}
+    cf = timings.get("fmd_cfconv_csr", [])
+    cf_ms = (sum(a.elapsed_time(bb) for a, bb in cf) / len(cf)) if cf else float("nan")
+    alg = E * F * b + 4 * N * F + 4 * N * F + 4 * E + 4 * E + 4 * (N + 1)
+    achieved = alg / (cf_ms * 1e-3) / 1e9
+    roof = {"kernel": "cfconv_csr_kernel (fmd_cfconv_csr)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+            "avg_launch_ms": cf_ms, "launches_per_step": len(cf) // reps, "peak_source": which,
+            "how": "CUDA events around each launch of an eager (non-graph) step, same stream, averaged over 3 steps"}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            roof["traffic"] = json.load(open(tp)).get("cfconv_csr_kernel")
+        except Exception:
+            pass
+    return roof, table
+
+
+if __name__ == "__main__":
+    main()

@@ -165,7 +165,10 @@ cfconv_csr_kernel(const float* __restrict__ x, const WT* __restrict__ filt, cons
   const int nw = (gridDim.x * blockDim.x) >> 5;
   for (int i = wid; i < n_nodes; i += nw) {
     const long long a = min((long long)seg_ptr[i], n_edges), b = min((long long)seg_ptr[i + 1], n_edges);
-    for (int f0 = lane * 4; f0 < F; f0 += 128) {
+    for (int fc = 0; fc < F; fc += 128) {
+      // every lane runs the loop (warp shuffles inside); lanes past F only skip the loads/stores
+      const int f0 = fc + lane * 4;
+      const bool fa = f0 < F;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (long long base = a; base < b; base += 32) {
         const long long p = base + lane;
@@ -193,8 +196,8 @@ cfconv_csr_kernel(const float* __restrict__ x, const WT* __restrict__ filt, cons
           float4 w[4], xv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            w[u] = load4_stream(filt + e[u] * F + f0);
-            xv[u] = load4(x + j[u] * F + f0);
+            w[u] = fa ? load4_stream(filt + e[u] * F + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[u] = fa ? load4(x + j[u] * F + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -205,7 +208,7 @@ cfconv_csr_kernel(const float* __restrict__ x, const WT* __restrict__ filt, cons
           }
         }
       }
-      store4(out + (size_t)i * F + f0, acc);
+      if (fa) store4(out + (size_t)i * F + f0, acc);
     }
   }
 }

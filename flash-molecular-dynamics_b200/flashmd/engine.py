@@ -454,3 +454,20 @@ def random_schnet_tensors(seed: int, num_rbf: int = 50, hidden: int = 128, filte
         if i < len(widths) - 2:
             t[f"out{i}_b"] = torch.zeros(widths[i + 1])
     return t
+
+
+def _step_host(self, pos_h, vel_h, forces_h, energy_h):
+    """End-to-end step with HOST state: pinned pos/vel/forces -> device, one BAOAB step, new
+    pos/vel/forces + per-molecule potential back to the pinned host buffers (synchronises)."""
+    self.pos.copy_(pos_h, non_blocking=True)
+    self.vel.copy_(vel_h, non_blocking=True)
+    self.ff.forces.copy_(forces_h, non_blocking=True)
+    self.step()
+    pos_h.copy_(self.pos, non_blocking=True)
+    vel_h.copy_(self.vel, non_blocking=True)
+    forces_h.copy_(self.ff.forces, non_blocking=True)
+    energy_h.copy_(self.ff.energy, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+
+
+LangevinEngine.step_host = _step_host
