@@ -42,6 +42,12 @@ _SIGS = {
                         c_int, c_float, c_void_p, c_void_p], c_int),
     "fmd_cfconv_grad_filter": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                 c_float, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
+    "fmd_filter_cfconv_fwd": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p], c_int),
+    "fmd_filter_cfconv_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
+                              c_int),
     "fmd_linear": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                     c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "fmd_embedding": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),

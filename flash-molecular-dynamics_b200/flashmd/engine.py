@@ -75,6 +75,12 @@ class SchNetWeights:
         for name in list(k.keys()):
             if ".f0_" in name or ".f1_" in name or name.startswith("out"):
                 k[name + ".h"] = k[name].half().contiguous()
+        # tensor-core operand of the fused filter kernels: Wf0 [F, num_rbf] zero-padded to 64 columns
+        if self.num_rbf <= 64:
+            for l in range(self.num_blocks):
+                wp = torch.zeros((self.filters, 64), dtype=torch.float16, device=dev)
+                wp[:, :self.num_rbf] = k[f"b{l}.f0_w.h"]
+                k[f"b{l}.f0_w.hp"] = wp.contiguous()
         self.k = k
         self.ones_col = None
 
@@ -111,7 +117,7 @@ class ForceField:
 
     def __init__(self, weights: Optional[SchNetWeights], priors: List[PriorTerm], atom_types: torch.Tensor,
                  mol_ptr: torch.Tensor, precision: str = "fp32", exact_cutoff_grad: bool = True,
-                 edge_capacity: Optional[int] = None, max_num_neighbors: int = 1000):
+                 edge_capacity: Optional[int] = None, max_num_neighbors: int = 1000, use_tensor_cores: bool = True):
         L.load()
         assert precision in ("fp32", "w16a16")
         self.w = weights
@@ -145,6 +151,9 @@ class ForceField:
             edge_capacity = int(per.sum().item())
         self.cap = cap = max(int(edge_capacity), 1)
         wdt = torch.float16 if precision == "w16a16" else f32
+        # W16A16 with the default widths runs the fused tcgen05 kernels (no [E,F] tensor in HBM);
+        # other widths / the fp32 parity path use the materialised SIMT kernels.
+        self.fused_tc = (precision == "w16a16" and F == 128 and H == 128 and R <= 64 and use_tensor_cores)
         self.deg = torch.zeros(N, dtype=i32, device=dev)
         self.seg_ptr = torch.zeros(N + 1, dtype=i32, device=dev)
         self.n_edges_dev = self.seg_ptr[N:]                      # int32[1] view: live edge count
@@ -153,13 +162,16 @@ class ForceField:
         self.dst = torch.zeros(cap, dtype=i32, device=dev)
         self.rev = torch.zeros(cap, dtype=i32, device=dev)
         self.dist = torch.zeros(cap, dtype=f32, device=dev)
-        self.rbf = torch.zeros((cap, R), dtype=f32, device=dev)
         nb = weights.num_blocks
-        self.t = [torch.zeros((cap, F), dtype=wdt, device=dev) for _ in range(nb)]
-        self.W = [torch.zeros((cap, F), dtype=wdt, device=dev) for _ in range(nb)]
-        self.gW = torch.zeros((cap, F), dtype=wdt, device=dev)
-        self.gT = torch.zeros((cap, F), dtype=wdt, device=dev)
-        self.g_rbf = torch.zeros((cap, R), dtype=f32, device=dev)
+        if self.fused_tc:
+            self.part = torch.zeros(((cap + 127) // 128, F), dtype=f32, device=dev)   # per-tile head partials
+        else:
+            self.rbf = torch.zeros((cap, R), dtype=f32, device=dev)
+            self.t = [torch.zeros((cap, F), dtype=wdt, device=dev) for _ in range(nb)]
+            self.W = [torch.zeros((cap, F), dtype=wdt, device=dev) for _ in range(nb)]
+            self.gW = torch.zeros((cap, F), dtype=wdt, device=dev)
+            self.gT = torch.zeros((cap, F), dtype=wdt, device=dev)
+            self.g_rbf = torch.zeros((cap, R), dtype=f32, device=dev)
         self.g_d = torch.zeros(cap, dtype=f32, device=dev)
         self.h = [torch.zeros((N, H), dtype=f32, device=dev) for _ in range(nb + 1)]
         self.a = [torch.zeros((N, F), dtype=f32, device=dev) for _ in range(nb)]
@@ -193,6 +205,24 @@ class ForceField:
                L.ptr(self.seg_ptr), None, 4, self.N, self.cap, x.shape[1], self.w.cutoff, L.ptr(out), self._st)
         self._n += 1
 
+    def _filter_cfconv(self, l, x, out):
+        """out[i] = sum_{e in seg(i)} W_l(d_e) * x[dst_e] * C(d_e): filter network + CFConv fused on tensor cores."""
+        w, k = self.w, self.w.k
+        L.call("fmd_filter_cfconv_fwd", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.seg_ptr), self.N,
+               self.cap, L.ptr(self.n_edges_dev), L.ptr(k[f"b{l}.f0_w.hp"]), L.ptr(k[f"b{l}.f0_b.h"]),
+               L.ptr(k[f"b{l}.f1_w.h"]), L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(x), w.filters,
+               L.ptr(out), L.ptr(self.part), None, None, self._st)
+        self._n += 2
+
+    def _filter_cfconv_bwd(self, l, a, g_m):
+        """g_d[e] += d/dd_e of sum_f g_m[src_e,f] W_l(d_e)[f] a[dst_e,f] C(d_e) (fused, tensor cores)."""
+        w, k = self.w, self.w.k
+        L.call("fmd_filter_cfconv_bwd", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), self.cap,
+               L.ptr(self.n_edges_dev), L.ptr(k[f"b{l}.f0_w.hp"]), L.ptr(k[f"b{l}.f0_b.h"]), L.ptr(k[f"b{l}.f1_w.h"]),
+               L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(a), L.ptr(g_m), w.filters, L.ptr(self.g_d), 1,
+               int(self.exact), self._st)
+        self._n += 1
+
     # -- neighbour list --------------------------------------------------------------------------
     def build_neighbor_list(self, pos):
         st, w = self._st, self.w
@@ -215,19 +245,25 @@ class ForceField:
         w16 = self.precision == "w16a16"
         nb, ned = w.num_blocks, self.n_edges_dev
         self.build_neighbor_list(pos)
-        # rbf [E,R] (distances were written by the neighbour-list fill)
-        L.call("fmd_dist_rbf_cutoff_fwd", L.ptr(pos), L.ptr(self.src), L.ptr(self.dst), 4, self.cap, L.ptr(ned),
-               L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, None, L.ptr(self.rbf), st)
+        tc = self.fused_tc
+        if not tc:
+            # rbf [E,R] (distances were written by the neighbour-list fill)
+            L.call("fmd_dist_rbf_cutoff_fwd", L.ptr(pos), L.ptr(self.src), L.ptr(self.dst), 4, self.cap, L.ptr(ned),
+                   L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, None, L.ptr(self.rbf), st)
+            self._n += 1
         L.call("fmd_embedding", L.ptr(k["embedding"]), L.ptr(self.types), 4, self.N, w.hidden, L.ptr(self.h[0]), st)
-        self._n += 2
+        self._n += 1
         tanh_f = L.ACT_TANH_CLAMPED if w16 else L.ACT_TANH
         sfx = ".h" if w16 else ""
         for l in range(nb):
             self._lin(self.h[l], k[f"b{l}.lin1_wT"], None, self.a[l])
-            self._lin(self.rbf, k[f"b{l}.f0_wT{sfx}"], k[f"b{l}.f0_b{sfx}"], self.t[l], m_dev=ned, x_round=w16,
-                      epi_act=tanh_f)
-            self._lin(self.t[l], k[f"b{l}.f1_wT{sfx}"], None, self.W[l], m_dev=ned)
-            self._cfconv(self.a[l], self.W[l], self.m)
+            if tc:
+                self._filter_cfconv(l, self.a[l], self.m)
+            else:
+                self._lin(self.rbf, k[f"b{l}.f0_wT{sfx}"], k[f"b{l}.f0_b{sfx}"], self.t[l], m_dev=ned, x_round=w16,
+                          epi_act=tanh_f)
+                self._lin(self.t[l], k[f"b{l}.f1_wT{sfx}"], None, self.W[l], m_dev=ned)
+                self._cfconv(self.a[l], self.W[l], self.m)
             self._lin(self.m, k[f"b{l}.lin2_wT"], k[f"b{l}.lin2_b"], self.c[l], epi_act=L.ACT_TANH)
             self._lin(self.c[l], k[f"b{l}.lin_wT"], k[f"b{l}.lin_b"], self.h[l + 1], res=self.h[l])
         # output network
@@ -257,6 +293,12 @@ class ForceField:
             # h_{l+1} = h_l + c Wl^T + bl ; c = tanh(m W2^T + b2)
             self._lin(gh_cur, k[f"b{l}.lin_w"], None, self.g_c, aux=self.c[l])
             self._lin(self.g_c, k[f"b{l}.lin2_w"], None, self.g_m)
+            if tc:
+                self._filter_cfconv(l, self.g_m, self.g_a)
+                self._filter_cfconv_bwd(l, self.a[l], self.g_m)
+                self._lin(self.g_a, k[f"b{l}.lin1_w"], None, gh_nxt, res=gh_cur)
+                gh_cur, gh_nxt = gh_nxt, gh_cur
+                continue
             # m[i] = sum_{e in seg(i)} a[dst_e] W_e C_e
             self._cfconv(self.g_m, self.W[l], self.g_a)
             L.call("fmd_cfconv_grad_filter", L.ptr(self.g_m), L.ptr(self.a[l]), L.ptr(self.dist), L.ptr(self.src),

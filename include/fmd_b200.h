@@ -134,6 +134,40 @@ int fmd_cfconv_grad_filter(const float* x, const float* g_out, const float* dist
                            int n_feat, float rc, void* g_filt, int ydt, const void* filt, int wdt,
                            float* g_dcut, int accumulate_dcut, void* stream);
 
+/* ---------------------------------------------------------------- fused filter network (x) CFConv (tensor cores) */
+
+/* replaces, for the W16A16 path, the chain  GPTQW16A16FilterNetwork.forward (models/gptq.py:92-130:
+ * fused_linear_tanh_fp16 kernels/cfconv_kernels.py:644-760 + linear_fp16_to_fp16 :896-952) ->
+ * fused_csr_cfconv (kernels/csr_kernels.py:625-810)  [and, with x = grad_out, fused_src_csr_grad_x :302-482]
+ * by ONE tcgen05 kernel per call: per 128-edge tile rbf is recomputed from dist, both filter GEMMs run on
+ * the tensor cores (fp16 operands, fp32 TMEM accumulators) and the messages are segment-reduced in the
+ * epilogue; t, W and rbf never reach HBM.
+ *   out[i,:] = sum_{e in [seg_ptr[i], seg_ptr[i+1])} (tanh(rbf_e Wf0^T + bf0) Wf1^T) * x[edge_nbr[e],:] * C(dist[e])
+ * Edge list: the sorted symmetric list of fmd_nl_fill (edge_owner = its edge_src, edge_nbr = its edge_dst,
+ * int32). wf0_h [128,64] fp16 = Wf0 [out,in] zero-padded from num_rbf to 64 columns; bf0_h [128] fp16 or
+ * NULL; wf1_h [128,128] fp16 [out,in]. n_feat must be 128, num_rbf <= 64. x, out [n_nodes,128] f32.
+ * part: scratch, >= ceil(capacity/128)*128 floats. dbg_t / dbg_w (nullable): dump t and W as [E,128] fp16.
+ * Deterministic, atomic-free. */
+int fmd_filter_cfconv_fwd(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr,
+                          const int32_t* seg_ptr, int n_nodes, int capacity, const int32_t* n_edges_dev,
+                          const void* wf0_h, const void* bf0_h, const void* wf1_h, const float* centers, int num_rbf,
+                          float gamma, float rc, const float* x, int n_feat, float* out, float* part, void* dbg_t,
+                          void* dbg_w, void* stream);
+
+/* replaces, for the W16A16 path, the edge part of FusedCSRCFConvFunction.backward + the filter network's
+ * backward + the fused-RBF backward: fused_grad_filter_out (kernels/cfconv_kernels.py:178-337),
+ * LinearFP16ToFP16Function / FusedLinearTanhFP16Function backward GEMMs (:963-1226, :1329-1434) and
+ * FusedDistanceGaussianRBFCutoffFunction.backward (:1679-1735, first half), in ONE tcgen05 kernel:
+ *   g_d[e] (+)= d/d(dist_e) sum_f g_m[owner_e,f] * W_e,f(dist_e) * a[nbr_e,f] * C(dist_e)
+ * through the radial basis (always) and through C (only when exact_cutoff_grad != 0; 0 reproduces the
+ * reference's Triton backward, kernels/csr_kernels.py:912). t is recomputed on the tensor cores, g_W, g_t
+ * are fp16 tensor-core operands (as in the reference) and never reach HBM. Same edge list / weight
+ * layout as fmd_filter_cfconv_fwd. a, g_m [n_nodes,128] f32. */
+int fmd_filter_cfconv_bwd(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr, int capacity,
+                          const int32_t* n_edges_dev, const void* wf0_h, const void* bf0_h, const void* wf1_h,
+                          const float* centers, int num_rbf, float gamma, float rc, const float* a, const float* g_m,
+                          int n_feat, float* g_d, int accumulate, int exact_cutoff_grad, void* stream);
+
 /* ---------------------------------------------------------------- dense layers -------------- */
 
 /* replaces: fused_tanh_linear (kernels/cfconv_kernels.py:1758-1941), fused_linear_tanh_fp16 (:644-760),

@@ -269,6 +269,31 @@ def test_schnet_w16a16(name):
     assert rel_l2(f.cpu(), g["ref64.forces.SchNet"]) < 2e-2
 
 
+@pytest.mark.parametrize("exact", [True, False])
+def test_fused_tensor_core_path_vs_materialised_path(exact):
+    """The tcgen05 fused filter-network x CFConv kernels (no [E,F] tensor in HBM) against the materialised
+    SIMT W16A16 pipeline on the same inputs: same rounding model up to tanh.approx / fp32-kept W, far
+    inside the 1e-2 bar; run-to-run bit-identical (no atomics)."""
+    from flashmd.engine import ForceField, SchNetWeights, random_schnet_tensors
+    from flashmd.synthetic import synthetic_system
+    B, n = 6, 269
+    sysd = synthetic_system(B, n, seed=3)
+    pos = torch.from_numpy(sysd["pos"]).reshape(B * n, 3).to(DEV).contiguous()
+    types = torch.from_numpy(sysd["atom_types"]).repeat(B).to(DEV)
+    ptr = (torch.arange(B + 1) * n).to(DEV)
+    w = SchNetWeights.from_flat(random_schnet_tensors(5), sysd["cutoff"], 50, DEV)
+    ff_tc = ForceField(w, [], types, ptr, precision="w16a16", exact_cutoff_grad=exact)
+    ff_mat = ForceField(w, [], types, ptr, precision="w16a16", exact_cutoff_grad=exact, use_tensor_cores=False)
+    assert ff_tc.fused_tc and not ff_mat.fused_tc
+    e1, f1 = [t.clone() for t in ff_tc.compute(pos)]
+    e2, f2 = [t.clone() for t in ff_mat.compute(pos)]
+    assert torch.isfinite(f1).all()
+    assert rel_l2(f1.cpu(), f2.cpu()) < 3e-3, rel_l2(f1.cpu(), f2.cpu())
+    assert rel_l2(e1.cpu(), e2.cpu()) < 3e-3
+    e3, f3 = ff_tc.compute(pos)
+    assert torch.equal(f1, f3) and torch.equal(e1, e3)
+
+
 def test_edge_capacity_and_large_batch_properties():
     """cfg2-shaped (B=128, n=269) run: size-independent properties — edge list symmetric and sorted,
     forces sum to zero per molecule (translation invariance), identical molecules give identical
