@@ -1,0 +1,158 @@
+// Classical prior terms, owner-computes form: one warp per bead walks the bead's incident terms
+// (static topology, CSR built once at set-up) and accumulates the bead's force and its share of the
+// term energies.  No atomics, deterministic; replaces the term-parallel atomicAdd kernel on the step
+// path (which serialised ~36 k repulsion pairs per molecule onto one energy address).
+//
+// Math per term (reference file:line):
+//   bonds      k (d - x0)^2 + V0          prior/harmonic.py:122-123, geometry/internal_coordinates.py:73-101
+//   repulsion  (sigma / d)^6              prior/repulsion.py:119-122
+//   angles     k (cos(theta) - x0)^2 + V0 prior/harmonic.py:122-123, internal_coordinates.py:140-170
+//   dihedrals  v0 + sum_n k1_n sin(n phi) + k2_n cos(n phi)   prior/fourier_series.py:154-192, :174-223
+// A term's energy is split evenly between its beads (1/2, 1/3, 1/4) so that the per-molecule sum
+// (fmd_segment_sum) reproduces scatter(y, mapping_batch) of the reference.
+#include "fmd_common.cuh"
+
+using namespace fmd;
+
+namespace {
+
+struct V3 {
+  float x, y, z;
+};
+__device__ __forceinline__ V3 ld3(const float* __restrict__ p, int i) {
+  return {__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)};
+}
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 add(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 mul(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+constexpr int WARPS = 8;
+
+__global__ void __launch_bounds__(WARPS * 32)
+prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __restrict__ pair_ptr,
+                 const int4* __restrict__ pair_ent, const int32_t* __restrict__ mb_ptr,
+                 const int32_t* __restrict__ mb_ent, const int32_t* __restrict__ ang_map, int n_ang,
+                 const float* __restrict__ ang_k, const float* __restrict__ ang_x0, const float* __restrict__ ang_v0,
+                 const int32_t* __restrict__ dih_map, int n_dih, const float* __restrict__ dih_k1,
+                 const float* __restrict__ dih_k2, const float* __restrict__ dih_v0, int n_degs,
+                 float* __restrict__ e_atom, float* __restrict__ forces, int accumulate_forces) {
+  const int lane = threadIdx.x & 31;
+  const int a = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (a >= n_nodes) return;
+  const V3 pa = ld3(pos, a);
+  V3 f = {0.f, 0.f, 0.f};
+  float e = 0.f;
+  // ---- two-body terms: entry = {other | kind << 28, p0, p1, p2}
+  if (pair_ptr) {
+    const int p1 = __ldg(&pair_ptr[a + 1]);
+    for (int p = __ldg(&pair_ptr[a]) + lane; p < p1; p += 32) {
+      const int4 ent = __ldg(&pair_ent[p]);
+      const int other = ent.x & 0x0FFFFFFF, kind = ent.x >> 28;
+      const float q0 = __int_as_float(ent.y), q1 = __int_as_float(ent.z), q2 = __int_as_float(ent.w);
+      const V3 dr = sub(ld3(pos, other), pa);
+      const float d = sqrtf(dot(dr, dr));
+      float et, dEdd;
+      if (kind == FMD_PRIOR_BONDS) {
+        et = q0 * (d - q1) * (d - q1) + q2;
+        dEdd = 2.0f * q0 * (d - q1);
+      } else {
+        const float sg = q0 / d, rr = sg * sg;
+        et = rr * rr * rr;
+        dEdd = -6.0f * et / d;
+      }
+      // d = |x_other - x_a|  =>  dE/dx_a = -dEdd * dr/d ;  force = +dEdd * dr/d
+      f = add(f, mul(dr, dEdd / d));
+      e += 0.5f * et;
+    }
+  }
+  // ---- three- and four-body terms: entry = term | role << 28 | is_dihedral << 30
+  if (mb_ptr) {
+    const int q1 = __ldg(&mb_ptr[a + 1]);
+    for (int q = __ldg(&mb_ptr[a]) + lane; q < q1; q += 32) {
+      const int ent = __ldg(&mb_ent[q]);
+      const int t = ent & 0x0FFFFFFF, role = (ent >> 28) & 3;
+      if (!((ent >> 30) & 1)) {
+        const int i = __ldg(&ang_map[t]), j = __ldg(&ang_map[n_ang + t]), k_ = __ldg(&ang_map[2 * n_ang + t]);
+        const V3 d1 = sub(ld3(pos, i), ld3(pos, j)), d2 = sub(ld3(pos, k_), ld3(pos, j));
+        const float n1 = sqrtf(dot(d1, d1)), n2 = sqrtf(dot(d2, d2));
+        const float inv = 1.0f / (n1 * n2);
+        const float c = dot(d1, d2) * inv;
+        const float k = __ldg(&ang_k[t]), x0 = __ldg(&ang_x0[t]);
+        const float et = k * (c - x0) * (c - x0) + (ang_v0 ? __ldg(&ang_v0[t]) : 0.f);
+        const float dEdc = 2.0f * k * (c - x0);
+        const V3 gi = mul(sub(mul(d2, inv), mul(d1, c / (n1 * n1))), dEdc);
+        const V3 gk = mul(sub(mul(d1, inv), mul(d2, c / (n2 * n2))), dEdc);
+        const V3 g = role == 0 ? gi : (role == 2 ? gk : mul(add(gi, gk), -1.f));
+        f = sub(f, g);
+        e += et * (1.0f / 3.0f);
+      } else {
+        const int i = __ldg(&dih_map[t]), j = __ldg(&dih_map[n_dih + t]), k_ = __ldg(&dih_map[2 * n_dih + t]),
+                  l = __ldg(&dih_map[3 * n_dih + t]);
+        const V3 b1 = sub(ld3(pos, j), ld3(pos, i)), b2 = sub(ld3(pos, k_), ld3(pos, j)),
+                 b3 = sub(ld3(pos, l), ld3(pos, k_));
+        const V3 m = cross(b1, b2), n = cross(b2, b3);
+        const float b2sq = dot(b2, b2), nb2 = sqrtf(b2sq);
+        const float phi = atan2f(nb2 * dot(b1, n), dot(m, n));
+        float dEdphi = 0.f;
+        float et = dih_v0 ? __ldg(&dih_v0[t]) : 0.f;
+        for (int d = 0; d < n_degs; ++d) {
+          float s, c;
+          sincosf((float)(d + 1) * phi, &s, &c);
+          const float k1 = __ldg(&dih_k1[(size_t)t * n_degs + d]), k2 = __ldg(&dih_k2[(size_t)t * n_degs + d]);
+          et += k1 * s + k2 * c;
+          dEdphi += (float)(d + 1) * (k1 * c - k2 * s);
+        }
+        const V3 gi = mul(m, -nb2 / dot(m, m));
+        const V3 gl = mul(n, nb2 / dot(n, n));
+        const float s_ = dot(b1, b2) / b2sq, t_ = dot(b3, b2) / b2sq;
+        V3 g;
+        if (role == 0) g = gi;
+        else if (role == 3) g = gl;
+        else if (role == 1) g = add(mul(gi, -1.f - s_), mul(gl, t_));
+        else g = add(mul(gl, -1.f - t_), mul(gi, s_));
+        f = sub(f, mul(g, dEdphi));
+        e += et * 0.25f;
+      }
+    }
+  }
+  f.x = warp_sum(f.x);
+  f.y = warp_sum(f.y);
+  f.z = warp_sum(f.z);
+  e = warp_sum(e);
+  if (lane == 0) {
+    if (accumulate_forces) {
+      forces[3 * a + 0] += f.x;
+      forces[3 * a + 1] += f.y;
+      forces[3 * a + 2] += f.z;
+    } else {
+      forces[3 * a + 0] = f.x;
+      forces[3 * a + 1] = f.y;
+      forces[3 * a + 2] = f.z;
+    }
+    e_atom[a] = e;
+  }
+}
+
+}  // namespace
+
+extern "C" int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair_ptr, const void* pair_ent,
+                              const int32_t* mb_ptr, const int32_t* mb_ent, const int32_t* ang_map, int n_ang,
+                              const float* ang_k, const float* ang_x0, const float* ang_v0, const int32_t* dih_map,
+                              int n_dih, const float* dih_k1, const float* dih_k2, const float* dih_v0, int n_degs,
+                              float* e_atom, float* forces, int accumulate_forces, void* stream) {
+  FMD_REQUIRE(pos && e_atom && forces, "fmd_priors_csr: bad arguments");
+  FMD_REQUIRE(!pair_ptr || pair_ent, "fmd_priors_csr: pair_ptr without pair entries");
+  FMD_REQUIRE(!mb_ptr || mb_ent, "fmd_priors_csr: mb_ptr without entries");
+  FMD_REQUIRE(n_ang == 0 || (ang_map && ang_k && ang_x0), "fmd_priors_csr: missing angle tables");
+  FMD_REQUIRE(n_dih == 0 || (dih_map && dih_k1 && dih_k2), "fmd_priors_csr: missing dihedral tables");
+  if (n_nodes <= 0) return FMD_OK;
+  prior_csr_kernel<<<fmd_div_up(n_nodes, WARPS), WARPS * 32, 0, (cudaStream_t)stream>>>(
+      pos, n_nodes, pair_ptr, (const int4*)pair_ent, mb_ptr, mb_ent, ang_map, n_ang, ang_k, ang_x0, ang_v0, dih_map,
+      n_dih, dih_k1, dih_k2, dih_v0, n_degs, e_atom, forces, accumulate_forces);
+  FMD_CHECK_LAUNCH();
+  return FMD_OK;
+}

@@ -107,6 +107,68 @@ class PriorTerm:
         return self.mapping.shape[1]
 
 
+class PriorCSR:
+    """Static incidence CSR of all prior terms (built once): what fmd_priors_csr consumes."""
+
+    def __init__(self, priors: List[PriorTerm], n_nodes: int, device):
+        i32 = torch.int32
+        self.n_nodes = n_nodes
+        own, rec = [], []
+        ang = [p for p in priors if p.kind == L.PRIOR_ANGLES]
+        dih = [p for p in priors if p.kind == L.PRIOR_DIHEDRALS]
+        assert len(ang) <= 1 and len(dih) <= 1, "condense priors first: at most one angle and one dihedral table"
+        for p in priors:
+            if p.kind not in (L.PRIOR_BONDS, L.PRIOR_REPULSION):
+                continue
+            i, j = p.mapping[0].long(), p.mapping[1].long()
+            assert int(p.mapping.max()) < (1 << 28)
+            z = torch.zeros_like(p.p0)
+            q1 = p.p1 if (p.kind == L.PRIOR_BONDS and p.p1 is not None) else z
+            q2 = p.p2 if (p.kind == L.PRIOR_BONDS and p.p2 is not None) else z
+            for a, b in ((i, j), (j, i)):
+                own.append(a)
+                rec.append(torch.stack([(b | (p.kind << 28)).to(i32), p.p0.float().view(i32), q1.float().view(i32),
+                                        q2.float().view(i32)], 1))
+        self.pair_ptr = self.pair_ent = None
+        if own:
+            own, rec = torch.cat(own), torch.cat(rec)
+            order = torch.argsort(own, stable=True)
+            self.pair_ent = rec[order].contiguous()
+            self.pair_ptr = self._ptr(own, n_nodes)
+        own, ent = [], []
+        for isd, group in ((0, ang), (1, dih)):
+            for p in group:
+                t = torch.arange(p.n_terms, device=device, dtype=torch.int64)
+                assert p.n_terms < (1 << 28)
+                for r in range(p.mapping.shape[0]):
+                    own.append(p.mapping[r].long())
+                    ent.append((t | (r << 28) | (isd << 30)).to(i32))
+        self.mb_ptr = self.mb_ent = None
+        if own:
+            own, ent = torch.cat(own), torch.cat(ent)
+            order = torch.argsort(own, stable=True)
+            self.mb_ent = ent[order].contiguous()
+            self.mb_ptr = self._ptr(own, n_nodes)
+        self.ang = ang[0] if ang else None
+        self.dih = dih[0] if dih else None
+        self.e_atom = torch.zeros(n_nodes, dtype=torch.float32, device=device)
+
+    @staticmethod
+    def _ptr(own, n_nodes):
+        cnt = torch.bincount(own, minlength=n_nodes)
+        ptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=own.device)
+        ptr[1:] = torch.cumsum(cnt, 0)
+        return ptr.to(torch.int32).contiguous()
+
+    def launch(self, pos, forces, accumulate, st):
+        a, d = self.ang, self.dih
+        L.call("fmd_priors_csr", L.ptr(pos), self.n_nodes, L.ptr(self.pair_ptr), L.ptr(self.pair_ent), L.ptr(self.mb_ptr),
+               L.ptr(self.mb_ent), L.ptr(a.mapping) if a else None, a.n_terms if a else 0, L.ptr(a.p0) if a else None,
+               L.ptr(a.p1) if a else None, L.ptr(a.p2) if a else None, L.ptr(d.mapping) if d else None,
+               d.n_terms if d else 0, L.ptr(d.p0) if d else None, L.ptr(d.p1) if d else None,
+               L.ptr(d.p2) if d else None, d.n_degs if d else 1, L.ptr(self.e_atom), L.ptr(forces), int(accumulate), st)
+
+
 # ------------------------------------------------------------------------------------------------
 # force field
 # ------------------------------------------------------------------------------------------------
@@ -140,6 +202,7 @@ class ForceField:
         self.energy = torch.zeros(B, dtype=f32, device=dev)
         self.forces = torch.zeros((N, 3), dtype=f32, device=dev)
         self.energy_terms: Dict[str, torch.Tensor] = {}
+        self.prior_csr = PriorCSR(priors, N, dev) if priors else None
         if weights is None:
             return
         F, R = weights.filters, weights.num_rbf
@@ -187,7 +250,6 @@ class ForceField:
                   for i, wd in enumerate(widths)]
         self.g_y = [torch.zeros((N, wd), dtype=odt, device=dev) for wd in widths[:-1]]
         self.ones = torch.ones((N, 1), dtype=odt, device=dev)
-        self.e_schnet = torch.zeros(B, dtype=f32, device=dev)
         self.launches_per_eval = 0
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -276,7 +338,7 @@ class ForceField:
                       epi_act=(L.ACT_NONE if last else tanh_f))
             x = self.y[i]
         assert self.y[-1].shape[1] == 1
-        L.call("fmd_segment_sum", L.ptr(self.y[-1]), L.ptr(self.mol_ptr), self.B, L.ptr(self.e_schnet), 0, st)
+        L.call("fmd_segment_sum", L.ptr(self.y[-1]), L.ptr(self.mol_ptr), self.B, L.ptr(self.energy), 0, st)
         self._n += 1
         # ---------------- backward
         # dE/d(e_atom) = 1  ->  through the output MLP
@@ -326,16 +388,17 @@ class ForceField:
         self._st = L.stream_ptr()
         self._n = 0
         if self.w is not None:
-            self._schnet(pos)
-            self.energy.copy_(self.e_schnet)
-        else:
+            self._schnet(pos)      # writes self.energy (per-molecule SchNet energy) and self.forces
+        elif self.prior_csr is None:
             self.energy.zero_()
             self.forces.zero_()
-        self._n += 2
-        for p in self.priors:
-            L.call("fmd_prior_energy_forces", p.kind, L.ptr(pos), L.ptr(p.mapping), L.ptr(p.mapping_batch), p.n_terms,
-                   L.ptr(p.p0), L.ptr(p.p1), L.ptr(p.p2), p.n_degs, L.ptr(self.energy), L.ptr(self.forces), self._st)
-            self._n += 1
+            self._n += 2
+        if self.prior_csr is not None:
+            # all prior classes in one owner-computes launch, then the per-molecule energy reduction
+            self.prior_csr.launch(pos, self.forces, self.w is not None, self._st)
+            L.call("fmd_segment_sum", L.ptr(self.prior_csr.e_atom), L.ptr(self.mol_ptr), self.B, L.ptr(self.energy),
+                   int(self.w is not None), self._st)
+            self._n += 2
         self.launches_per_eval = self._n
         return self.energy, self.forces
 

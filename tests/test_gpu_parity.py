@@ -241,6 +241,24 @@ def test_prior_terms(kind):
         assert rel_l2(val.cpu(), r32) < tol, (what, rel_l2(val.cpu(), r32), tol)
 
 
+@pytest.mark.parametrize("kind", ["bonds", "angles", "dihedrals", "repulsion"])
+def test_prior_terms_term_parallel_kernel(kind):
+    """The operator-level, term-parallel entry point (fmd_prior_energy_forces, atomicAdd like the
+    reference's index_add_) against the same golden values as the owner-computes step kernel."""
+    from flashmd import _lib as L
+    g = load_golden("schnet_n54_b4.npz")
+    ff, pos = _engine_from_golden(g, "fp32", priors=True)
+    p = ff.priors[["bonds", "angles", "dihedrals", "repulsion"].index(kind)]
+    e = torch.zeros(ff.B, device=DEV)
+    f = torch.zeros((ff.N, 3), device=DEV)
+    L.call("fmd_prior_energy_forces", p.kind, L.ptr(pos), L.ptr(p.mapping), L.ptr(p.mapping_batch), p.n_terms,
+           L.ptr(p.p0), L.ptr(p.p1), L.ptr(p.p2), p.n_degs, L.ptr(e), L.ptr(f), L.stream_ptr())
+    for what, val in (("energy", e), ("forces", f)):
+        r32, r64 = g[f"ref32.{what}.{kind}"], g[f"ref64.{what}.{kind}"]
+        tol = max(1e-5, 2.0 * rel_l2(r32, r64))
+        assert rel_l2(val.cpu(), r64) < tol, (what, rel_l2(val.cpu(), r64), tol)
+
+
 def test_schnet_triton_compat_mode_drops_cutoff_gradient():
     """exact_cutoff_grad=False reproduces the reference Triton backward (csr_kernels.py:912)."""
     g = load_golden("schnet_n54_b4.npz")
