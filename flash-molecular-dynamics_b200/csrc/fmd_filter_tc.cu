@@ -19,23 +19,13 @@
 //
 // Edges are sorted by their segment owner (fmd_nl_fill order); a segment that straddles tiles is
 // completed by a tiny fix-up kernel from per-tile "head" partial sums in a fixed order: no atomics.
-#include "fmd_tc.cuh"
+#include "fmd_filter_shared.cuh"
 
 using namespace fmd;
 using namespace fmd::tc;
+using namespace fmd::filt;
 
 namespace {
-
-constexpr int TILE = 128;  // edges per tile == threads per CTA == features
-constexpr int NF = 128;    // filters / hidden width handled by this kernel
-constexpr int RP = 64;     // num_rbf padded to a multiple of 16 (MMA K step)
-
-struct __align__(16) EdgeMeta {
-  int32_t owner;  // segment owner (edge_src)
-  int32_t nbr;    // gathered node (edge_dst)
-  float cut;      // C(d_e)
-  float dist;
-};
 
 // shared-memory map (offsets from a 1024-byte aligned base)
 constexpr uint32_t OFF_WF0 = 0;                      // 16 KB
@@ -49,38 +39,6 @@ constexpr uint32_t OFF_BAR = OFF_CEN + RP * 4;       // mbarriers (8 B each at +
 constexpr uint32_t OFF_RED = OFF_BAR + 32;           // 2 KB: per-warp partial sums of the cut-off term (bwd)
 constexpr uint32_t FWD_SMEM = OFF_RED + 4 * TILE * 4;
 constexpr uint32_t FWD_SMEM_ALLOC = FWD_SMEM + 1024;  // alignment slack
-
-// copy a [rows][ncols16 * 8 halves] fp16 row-major global matrix into K-major swizzle-128B blocks of
-// [rows][64 halves] (block kb holds columns 64*kb .. 64*kb+63, blocks are rows*128 bytes apart)
-__device__ __forceinline__ void load_weight_kmajor(uint8_t* dst, const __half* __restrict__ src, int rows, int ncols16) {
-  const int total = rows * ncols16;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int r = idx / ncols16, c = idx - r * ncols16;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + idx);
-    const int kb = c >> 3, cc = c & 7;
-    *reinterpret_cast<uint4*>(dst + kb * rows * 128 + sw128_off(r, cc)) = v;
-  }
-}
-
-// thread e: radial basis of its edge -> row e of the K-major B operand (fp16, the reference's in-kernel
-// cast kernels/cfconv_kernels.py:701); rbf_k = exp(gamma (d-mu_k)^2) * C(d)  (radial_basis/gaussian.py:83-102)
-__device__ __forceinline__ void write_rbf_row(uint8_t* sRbf, const float* sCen, int row, float d, float cut, int R,
-                                              float gamma, bool valid) {
-#pragma unroll
-  for (int c = 0; c < RP / 8; ++c) {
-    uint32_t p[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k0 = c * 8 + 2 * u;
-      const float d0 = d - sCen[k0], d1 = d - sCen[k0 + 1];
-      float v0 = __expf(gamma * d0 * d0) * cut, v1 = __expf(gamma * d1 * d1) * cut;
-      if (!valid || k0 >= R) v0 = 0.f;
-      if (!valid || k0 + 1 >= R) v1 = 0.f;
-      p[u] = pack_half2(v0, v1);
-    }
-    *reinterpret_cast<uint4*>(sRbf + sw128_off(row, c)) = make_uint4(p[0], p[1], p[2], p[3]);
-  }
-}
 
 template <bool kDump>
 __global__ void __launch_bounds__(TILE, 2)
@@ -496,6 +454,11 @@ cfconv_fixup_kernel(const int32_t* __restrict__ seg_ptr, int n_nodes, int capaci
 }
 
 }  // namespace
+
+void fmd_cfconv_fixup_launch(const int32_t* seg_ptr, int n_nodes, int capacity, const float* part, float* out,
+                             cudaStream_t st) {
+  cfconv_fixup_kernel<<<fmd_div_up((long long)n_nodes * 32, 256), 256, 0, st>>>(seg_ptr, n_nodes, capacity, part, out);
+}
 
 extern "C" int fmd_filter_cfconv_fwd(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr,
                                      const int32_t* seg_ptr, int n_nodes, int capacity, const int32_t* n_edges_dev,

@@ -1,0 +1,297 @@
+// Warp-specialised, software-pipelined version of the fused filter-network (x) CFConv forward kernel
+// (see fmd_filter_tc.cu for the math and the transposed formulation).  One persistent CTA per SM,
+// 17 warps in five roles connected by mbarrier rings, so the phases of consecutive 128-edge tiles overlap:
+//
+//   P  warps 0-3    thread-per-edge: metadata prefetch, radial basis row -> sRbf[2], sMeta[4]
+//   M  warp  4      one thread issues tcgen05.mma:  D1[s] = Wf0 . rbf^T ,  D2[s] = Wf1 . t^T
+//   T  warps 5-8    thread-per-feature: D1[s] -> tanh -> fp16 row of t^T -> sTT[2]
+//   E0 warps 9-12   thread-per-feature epilogue of even tiles: D2[0] * x[nbr] * C -> segment sums
+//   E1 warps 13-16  same for odd tiles (D2[1]); two groups hide the gather latency of x
+//
+// TMEM: D1[2] + D2[2] = 512 columns.  smem: weights 48 KB + sRbf 2x16 KB + sTT 2x32 KB + meta.
+#include "fmd_filter_shared.cuh"
+
+using namespace fmd;
+using namespace fmd::tc;
+using namespace fmd::filt;
+
+namespace {
+
+constexpr int NTHREADS = 17 * 32;
+constexpr int META_STAGES = 4;
+
+constexpr uint32_t O_WF0 = 0;                                // 16 KB
+constexpr uint32_t O_WF1 = O_WF0 + 128 * 128;                // 32 KB
+constexpr uint32_t O_RBF = O_WF1 + 2 * 128 * 128;            // 2 x 16 KB
+constexpr uint32_t O_TT = O_RBF + 2 * 128 * 128;             // 2 x 32 KB
+constexpr uint32_t O_META = O_TT + 2 * 2 * 128 * 128;        // 4 x 1 KB: {x offset, C(d)} per edge
+constexpr uint32_t O_OWN = O_META + META_STAGES * TILE * 8;  // 4 x 512 B: segment owner per edge
+constexpr uint32_t O_HEAD = O_OWN + META_STAGES * TILE * 4;  // 4 x 32 B: {prev_owner, -, -, -, boundary mask[4]}
+constexpr uint32_t O_BIAS = O_HEAD + META_STAGES * 32;
+constexpr uint32_t O_CEN = O_BIAS + NF * 4;
+constexpr uint32_t O_BAR = O_CEN + RP * 4;                   // 24 mbarriers + tmem slot
+constexpr uint32_t SMEM2 = O_BAR + 24 * 8 + 16;
+constexpr uint32_t SMEM2_ALLOC = SMEM2 + 1024;
+
+// barrier indices
+enum { B_RBF_FULL = 0, B_RBF_EMPTY = 2, B_D1_FULL = 4, B_D1_EMPTY = 6, B_TT_FULL = 8, B_TT_EMPTY = 10,
+       B_D2_FULL = 12, B_D2_EMPTY = 14, B_META_EMPTY = 16, B_COUNT = 20 };
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restrict__ edge_owner,
+                          const int32_t* __restrict__ edge_nbr, int capacity,
+                          const int32_t* __restrict__ n_edges_dev, const __half* __restrict__ wf0,
+                          const __half* __restrict__ bf0, const __half* __restrict__ wf1,
+                          const float* __restrict__ centers, int R, float gamma, float rc,
+                          const float* __restrict__ x, float* __restrict__ out, float* __restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sBias = reinterpret_cast<float*>(smem + O_BIAS);
+  float* sCen = reinterpret_cast<float*>(smem + O_CEN);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + O_BAR + 24 * 8);
+  auto bar = [&](int i) { return sbase + O_BAR + 8u * (uint32_t)i; };
+
+  const int E = min(capacity, n_edges_dev ? *n_edges_dev : capacity);
+  const int n_tiles = (E + TILE - 1) / TILE;
+  const int n_my = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  // ---- one-time setup
+  load_weight_kmajor(smem + O_WF0, wf0, NF, RP / 8);
+  load_weight_kmajor(smem + O_WF1, wf1, NF, NF / 8);
+  if (tid < NF) sBias[tid] = bf0 ? __half2float(bf0[tid]) : 0.f;
+  if (tid < RP) sCen[tid] = tid < R ? centers[tid] : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(B_RBF_FULL + i), 128);
+      mbar_init(bar(B_RBF_EMPTY + i), 1);
+      mbar_init(bar(B_D1_FULL + i), 1);
+      mbar_init(bar(B_D1_EMPTY + i), 128);
+      mbar_init(bar(B_TT_FULL + i), 128);
+      mbar_init(bar(B_TT_EMPTY + i), 1);
+      mbar_init(bar(B_D2_FULL + i), 1);
+      mbar_init(bar(B_D2_EMPTY + i), 128);
+    }
+    for (int i = 0; i < META_STAGES; ++i) mbar_init(bar(B_META_EMPTY + i), 128);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(sbase + O_BAR + 24 * 8, 512);
+  }
+  fence_async_smem();  // weights were written through the generic proxy
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // =========================================================== P: producers (thread = edge row)
+    const float g2 = gamma * 1.4426950408889634f;
+    const float pi_over_rc = FMD_PI_F / rc;
+    int tile = blockIdx.x;
+    float d_n = 0.f;
+    int own_n = 0, nbr_n = 0, prev_n = -1;
+    auto prefetch = [&](int t) {
+      const int e = t * TILE + tid;
+      d_n = 0.f; own_n = -1; nbr_n = 0; prev_n = -1;
+      if (e < E) {
+        d_n = __ldg(&dist[e]);
+        own_n = __ldg(&edge_owner[e]);
+        nbr_n = __ldg(&edge_nbr[e]);
+        if (e > 0) prev_n = __ldg(&edge_owner[e - 1]);
+      }
+    };
+    if (n_my > 0) prefetch(tile);
+    for (int i = 0; i < n_my; ++i, tile += gridDim.x) {
+      const int s = i & 1, ms = i & (META_STAGES - 1);
+      const uint32_t ph = (i >> 1) & 1, mph = (i / META_STAGES) & 1;
+      const float d = d_n;
+      const int own = own_n, nb = nbr_n, prev = prev_n;
+      if (i + 1 < n_my) prefetch(tile + gridDim.x);
+      const bool valid = own >= 0;
+      const float cut = valid ? cosine_cutoff_fast(d, pi_over_rc, rc) : 0.f;
+      // segment boundary inside the tile: this edge starts a new owner's run (tile-local edge 0 is the "head")
+      const uint32_t bmask = __ballot_sync(0xffffffffu, valid && tid > 0 && own != prev);
+      mbar_wait_guard(bar(B_META_EMPTY + ms), mph ^ 1);
+      mbar_wait_guard(bar(B_RBF_EMPTY + s), ph ^ 1);
+      reinterpret_cast<uint2*>(smem + O_META + ms * TILE * 8)[tid] =
+          make_uint2((uint32_t)nb * (uint32_t)NF, __float_as_uint(cut));
+      reinterpret_cast<int*>(smem + O_OWN + ms * TILE * 4)[tid] = own;
+      if (tid == 0) *reinterpret_cast<int*>(smem + O_HEAD + ms * 32) = prev;
+      if (lane == 0) reinterpret_cast<uint32_t*>(smem + O_HEAD + ms * 32 + 16)[warp] = bmask;
+      write_rbf_row_fast(smem + O_RBF + s * (128 * 128), sCen, tid, d, cut, g2);
+      fence_async_smem();
+      mbar_arrive(bar(B_RBF_FULL + s));
+    }
+  } else if (warp == 4) {
+    // =========================================================== M: MMA issuer (one thread)
+    if (lane == 0 && n_my > 0) {
+      constexpr uint32_t IDESC1 = idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t IDESC2 = idesc_f16(128, 128, 0, 1);
+      const uint64_t dA1 = smem_desc_sw128(sbase + O_WF0, 16, 1024);
+      const uint64_t dA2 = smem_desc_sw128(sbase + O_WF1, 16, 1024);
+      auto issue1 = [&](int i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait_guard(bar(B_RBF_FULL + s), ph);
+        mbar_wait_guard(bar(B_D1_EMPTY + s), ph ^ 1);
+        fence_after_sync();
+        const uint64_t dB1 = smem_desc_sw128(sbase + O_RBF + s * (128 * 128), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < RP / 16; ++k) mma_f16(tmem + s * 128, dA1 + 2 * k, dB1 + 2 * k, IDESC1, k > 0);
+        mma_commit(bar(B_RBF_EMPTY + s));
+        mma_commit(bar(B_D1_FULL + s));
+      };
+      auto issue2 = [&](int i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait_guard(bar(B_TT_FULL + s), ph);
+        mbar_wait_guard(bar(B_D2_EMPTY + s), ph ^ 1);
+        fence_after_sync();
+        const uint64_t dB2 = smem_desc_sw128(sbase + O_TT + s * (2 * 128 * 128), 128 * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < NF / 16; ++k)
+          mma_f16(tmem + 256 + s * 128, dA2 + (uint64_t)((k >> 2) * (128 * 128 / 16) + (k & 3) * 2),
+                  dB2 + (uint64_t)(k * (2048 / 16)), IDESC2, k > 0);
+        mma_commit(bar(B_TT_EMPTY + s));
+        mma_commit(bar(B_D2_FULL + s));
+      };
+      issue1(0);
+      for (int i = 0; i < n_my; ++i) {
+        if (i + 1 < n_my) issue1(i + 1);
+        issue2(i);
+      }
+    }
+  } else if (warp < 9) {
+    // =========================================================== T: tanh (thread = feature j)
+    const int j = (warp & 3) * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    const float bias = sBias[j];
+    for (int i = 0; i < n_my; ++i) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      mbar_wait_guard(bar(B_D1_FULL + s), ph);
+      mbar_wait_guard(bar(B_TT_EMPTY + s), ph ^ 1);
+      fence_after_sync();
+      uint8_t* sTT = smem + O_TT + s * (2 * 128 * 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + s * 128 + lane_sel + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t p[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            p[u] = pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u]) + bias),
+                              tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]) + bias));
+          const int chunk = c * 4 + q;
+          *reinterpret_cast<uint4*>(sTT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7)) =
+              make_uint4(p[0], p[1], p[2], p[3]);
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(bar(B_D1_EMPTY + s));
+      fence_async_smem();
+      mbar_arrive(bar(B_TT_FULL + s));
+    }
+  } else {
+    // =========================================================== E0 / E1: epilogue (thread = feature f)
+    const int g = warp < 13 ? 0 : 1;
+    const int f = (warp & 3) * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    const float* __restrict__ xf = x + f;
+    for (int i = g; i < n_my; i += 2) {
+      const int ms = i & (META_STAGES - 1);
+      const uint32_t ph = (i >> 1) & 1;
+      const int tile = blockIdx.x + i * gridDim.x;
+      const uint4* sMeta2 = reinterpret_cast<const uint4*>(smem + O_META + ms * TILE * 8);  // two edges per uint4
+      const int* sOwn = reinterpret_cast<const int*>(smem + O_OWN + ms * TILE * 4);
+      const uint32_t* sMask = reinterpret_cast<const uint32_t*>(smem + O_HEAD + ms * 32 + 16);
+      mbar_wait_guard(bar(B_D2_FULL + g), ph);
+      fence_after_sync();
+      int cur = sOwn[0];
+      bool head = *reinterpret_cast<const int*>(smem + O_HEAD + ms * 32) == cur;  // run began in an earlier tile
+      float acc = 0.f;
+      auto flush = [&](int next_owner) {
+        if (head) part[(size_t)tile * NF + f] = acc;
+        else out[(size_t)cur * NF + f] = acc;
+        head = false;
+        cur = next_owner;
+        acc = 0.f;
+      };
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + 256 + g * 128 + lane_sel + c * 32, r);
+        float xv[32];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const uint4 m = sMeta2[c * 16 + u];
+          xv[2 * u] = __ldg(xf + m.x) * __uint_as_float(m.y);
+          xv[2 * u + 1] = __ldg(xf + m.z) * __uint_as_float(m.w);
+        }
+        const uint32_t bits = sMask[c];
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (((bits >> (8 * q)) & 0xffu) == 0u) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fmaf(__uint_as_float(r[q * 8 + u]), xv[q * 8 + u], acc);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if ((bits >> (8 * q + u)) & 1u) flush(sOwn[c * 32 + q * 8 + u]);
+              acc = fmaf(__uint_as_float(r[q * 8 + u]), xv[q * 8 + u], acc);
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(bar(B_D2_EMPTY + g));
+      mbar_arrive(bar(B_META_EMPTY + ms));
+      flush(0);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+// defined in fmd_filter_tc.cu
+void fmd_cfconv_fixup_launch(const int32_t* seg_ptr, int n_nodes, int capacity, const float* part, float* out,
+                             cudaStream_t st);
+
+extern "C" int fmd_filter_cfconv_fwd2(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr,
+                                      const int32_t* seg_ptr, int n_nodes, int capacity, const int32_t* n_edges_dev,
+                                      const void* wf0_h, const void* bf0_h, const void* wf1_h, const float* centers,
+                                      int num_rbf, float gamma, float rc, const float* x, int n_feat, float* out,
+                                      float* part, void* stream) {
+  FMD_REQUIRE(dist && edge_owner && edge_nbr && seg_ptr && wf0_h && wf1_h && centers && x && out && part,
+              "fmd_filter_cfconv_fwd2: null argument");
+  FMD_REQUIRE(n_feat == NF && num_rbf > 0 && num_rbf <= RP, "fmd_filter_cfconv_fwd2: needs F == 128 and num_rbf <= 64");
+  if (n_nodes <= 0) return FMD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FMD_CUDA(cudaFuncSetAttribute(filter_cfconv_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)SMEM2_ALLOC));
+    attr_done = true;
+  }
+  if (capacity > 0) {
+    const int max_tiles = fmd_div_up(capacity, TILE);
+    const int grid = max_tiles < fmd_num_sms() ? max_tiles : fmd_num_sms();
+    filter_cfconv_fwd2_kernel<<<grid, NTHREADS, SMEM2_ALLOC, st>>>(
+        dist, edge_owner, edge_nbr, capacity, n_edges_dev, (const __half*)wf0_h, (const __half*)bf0_h,
+        (const __half*)wf1_h, centers, num_rbf, gamma, rc, x, out, part);
+    FMD_CHECK_LAUNCH();
+  }
+  fmd_cfconv_fixup_launch(seg_ptr, n_nodes, capacity, part, out, st);
+  FMD_CHECK_LAUNCH();
+  return FMD_OK;
+}

@@ -45,6 +45,9 @@ _SIGS = {
     "fmd_filter_cfconv_fwd": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p], c_int),
+    "fmd_filter_cfconv_fwd2": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p,
+                                c_void_p], c_int),
     "fmd_filter_cfconv_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
                               c_int),

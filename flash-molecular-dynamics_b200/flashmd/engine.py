@@ -270,10 +270,10 @@ class ForceField:
     def _filter_cfconv(self, l, x, out):
         """out[i] = sum_{e in seg(i)} W_l(d_e) * x[dst_e] * C(d_e): filter network + CFConv fused on tensor cores."""
         w, k = self.w, self.w.k
-        L.call("fmd_filter_cfconv_fwd", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.seg_ptr), self.N,
+        L.call("fmd_filter_cfconv_fwd2", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.seg_ptr), self.N,
                self.cap, L.ptr(self.n_edges_dev), L.ptr(k[f"b{l}.f0_w.hp"]), L.ptr(k[f"b{l}.f0_b.h"]),
                L.ptr(k[f"b{l}.f1_w.h"]), L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(x), w.filters,
-               L.ptr(out), L.ptr(self.part), None, None, self._st)
+               L.ptr(out), L.ptr(self.part), self._st)
         self._n += 2
 
     def _filter_cfconv_bwd(self, l, a, g_m):

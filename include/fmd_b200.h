@@ -154,6 +154,14 @@ int fmd_filter_cfconv_fwd(const float* dist, const int32_t* edge_owner, const in
                           float gamma, float rc, const float* x, int n_feat, float* out, float* part, void* dbg_t,
                           void* dbg_w, void* stream);
 
+/* Same contract as fmd_filter_cfconv_fwd (without the debug dumps): the warp-specialised, software-pipelined
+ * kernel used on the step path - one persistent CTA per SM, producer / MMA-issuer / tanh / epilogue warps
+ * connected by mbarrier rings, D1 and D2 double-buffered in TMEM (512 columns). */
+int fmd_filter_cfconv_fwd2(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr,
+                           const int32_t* seg_ptr, int n_nodes, int capacity, const int32_t* n_edges_dev,
+                           const void* wf0_h, const void* bf0_h, const void* wf1_h, const float* centers, int num_rbf,
+                           float gamma, float rc, const float* x, int n_feat, float* out, float* part, void* stream);
+
 /* replaces, for the W16A16 path, the edge part of FusedCSRCFConvFunction.backward + the filter network's
  * backward + the fused-RBF backward: fused_grad_filter_out (kernels/cfconv_kernels.py:178-337),
  * LinearFP16ToFP16Function / FusedLinearTanhFP16Function backward GEMMs (:963-1226, :1329-1434) and

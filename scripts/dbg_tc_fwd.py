@@ -54,9 +54,32 @@ def run(sizes, box, rc, R=50, seed=0, verbose=True):
 
     def rel(a, b):
         return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
-    res = {"E": E, "t": rel(dbg_t[:E], t), "W": rel(dbg_w[:E], W), "m": rel(out, m),
+    out2 = torch.full((N, F), float("nan"), device=dev)
+    part2 = torch.zeros((ntile, F), device=dev)
+
+    def fwd2():
+        L.call("fmd_filter_cfconv_fwd2", L.ptr(dist), L.ptr(src), L.ptr(dst), L.ptr(seg), N, E, None, L.ptr(wf0p),
+               L.ptr(bf0h), L.ptr(wf1h), L.ptr(centers), R, gamma, float(rc), L.ptr(x), F, L.ptr(out2), L.ptr(part2),
+               L.stream_ptr())
+    fwd2()
+    torch.cuda.synchronize()
+    res = {"E": E, "m2": rel(out2, m), "nan2": int(torch.isnan(out2).sum()), "t": rel(dbg_t[:E], t), "W": rel(dbg_w[:E], W), "m": rel(out, m),
            "t_max": float((dbg_t[:E].float() - t.float()).abs().max()) if E else 0.0,
            "nan": int(torch.isnan(out).sum())}
+    if E > 100000:
+        for _ in range(3):
+            fwd2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fwd2()
+        e1.record()
+        torch.cuda.synchronize()
+        res["fwd2_ms"] = e0.elapsed_time(e1) / 20
+        out3 = out2.clone()
+        fwd2()
+        torch.cuda.synchronize()
+        res["deterministic"] = bool(torch.equal(out2, out3))
     if verbose:
         print(sizes[:4], "rc", rc, res)
     return res
@@ -64,7 +87,12 @@ def run(sizes, box, rc, R=50, seed=0, verbose=True):
 
 if __name__ == "__main__":
     L.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        run([269] * 128, 24.0, 10.5)
+        sys.exit(0)
     run([54] * 4, 14.0, 6.0)
     run([1, 2, 33, 7, 130, 64], 10.0, 3.5)
     run([300], 6.0, 50.0)          # degree 299: segments straddle 3 tiles
     run([269] * 128, 24.0, 7.5)
+    run([269] * 128, 24.0, 10.5)
+    run([100], 5.0, 3.0)
