@@ -261,6 +261,370 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// =================================================================================================
+// Backward (see fmd_filter_tc.cu for the math), warp-specialised:
+//   PE warps 0-3   thread-per-edge: produce(i) = metadata + rbf row; e4(i-2) = D4 -> g_d
+//   G0 warps 4-7   thread-per-feature: row f of gW0^T = a[nbr,f] * g_m[owner,f] for even tiles
+//   G1 warps 8-11  same for odd tiles
+//   T  warps 12-15 thread-per-feature: A(i) = D1 -> t (stashed in smem); B(i) = D3 -> g_t row + cut-term sums
+//   M  warp  16    MMA issue: D13[s] = Wf0.rbf^T ; D13[s] = Wf1^T.gW0^T ; D4[s] = g_t.Wf0
+constexpr uint32_t BO_WF0 = 0;
+constexpr uint32_t BO_WF1 = BO_WF0 + 128 * 128;
+constexpr uint32_t BO_RBF = BO_WF1 + 2 * 128 * 128;          // 2 x 16 KB
+constexpr uint32_t BO_OP = BO_RBF + 2 * 128 * 128;           // 2 x 32 KB: gW0^T, then g_t^T
+constexpr uint32_t BO_ST = BO_OP + 2 * 2 * 128 * 128;        // 2 x 32 KB: t^T stash
+constexpr uint32_t BO_META = BO_ST + 2 * 2 * 128 * 128;      // 4 x 1 KB
+constexpr uint32_t BO_OWN = BO_META + META_STAGES * TILE * 8;
+constexpr uint32_t BO_HEAD = BO_OWN + META_STAGES * TILE * 4;  // 4 x 16 B boundary masks
+constexpr uint32_t BO_RED = BO_HEAD + META_STAGES * 16;      // 2 x [4][128] floats
+constexpr uint32_t BO_BIAS = BO_RED + 2 * 4 * TILE * 4;
+constexpr uint32_t BO_CEN = BO_BIAS + NF * 4;
+constexpr uint32_t BO_BAR = BO_CEN + RP * 4;
+constexpr uint32_t BSMEM = BO_BAR + 40 * 8 + 16;
+constexpr uint32_t BSMEM_ALLOC = BSMEM + 1024;
+static_assert(BSMEM_ALLOC <= 232448, "backward kernel exceeds the 227 KB shared-memory limit");
+
+enum { C_RBF_FULL = 0, C_RBF_EMPTY = 2, C_D1_FULL = 4, C_D1_EMPTY = 6, C_GW_FULL = 8, C_D3_FULL = 10, C_D3_EMPTY = 12,
+       C_GT_FULL = 14, C_OP_EMPTY = 16, C_D4_FULL = 18, C_D4_EMPTY = 20, C_META_FULL = 22, C_META_EMPTY = 26,
+       C_COUNT = 30 };
+
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+
+template <bool kExact>
+__global__ void __launch_bounds__(NTHREADS, 1)
+filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restrict__ edge_owner,
+                          const int32_t* __restrict__ edge_nbr, int capacity,
+                          const int32_t* __restrict__ n_edges_dev, const __half* __restrict__ wf0,
+                          const __half* __restrict__ bf0, const __half* __restrict__ wf1,
+                          const float* __restrict__ centers, int R, float gamma, float rc,
+                          const float* __restrict__ a, const float* __restrict__ g_m, float* __restrict__ g_d,
+                          int accumulate) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sBias = reinterpret_cast<float*>(smem + BO_BIAS);
+  float* sCen = reinterpret_cast<float*>(smem + BO_CEN);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + BO_BAR + 40 * 8);
+  auto bar = [&](int i) { return sbase + BO_BAR + 8u * (uint32_t)i; };
+
+  const int E = min(capacity, n_edges_dev ? *n_edges_dev : capacity);
+  const int n_tiles = (E + TILE - 1) / TILE;
+  const int n_my = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  load_weight_kmajor(smem + BO_WF0, wf0, NF, RP / 8);
+  load_weight_kmajor(smem + BO_WF1, wf1, NF, NF / 8);
+  if (tid < NF) sBias[tid] = bf0 ? __half2float(bf0[tid]) : 0.f;
+  if (tid < RP) sCen[tid] = tid < R ? centers[tid] : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(C_RBF_FULL + i), 128);
+      mbar_init(bar(C_RBF_EMPTY + i), 1);
+      mbar_init(bar(C_D1_FULL + i), 1);
+      mbar_init(bar(C_D1_EMPTY + i), 128);
+      mbar_init(bar(C_GW_FULL + i), 128);
+      mbar_init(bar(C_D3_FULL + i), 1);
+      mbar_init(bar(C_D3_EMPTY + i), 128);
+      mbar_init(bar(C_GT_FULL + i), 128);
+      mbar_init(bar(C_OP_EMPTY + i), 1);
+      mbar_init(bar(C_D4_FULL + i), 1);
+      mbar_init(bar(C_D4_EMPTY + i), 128);
+    }
+    for (int i = 0; i < META_STAGES; ++i) {
+      mbar_init(bar(C_META_FULL + i), 128);
+      mbar_init(bar(C_META_EMPTY + i), 256);  // the G group and T both consume the metadata
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(sbase + BO_BAR + 40 * 8, 512);
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: D13[s] at s*128, D4[s] at 256 + s*64
+
+  if (warp < 4) {
+    // =========================================================== PE: produce(i), then e4(i-2)
+    const float g2 = gamma * 1.4426950408889634f;
+    const float pi_over_rc = FMD_PI_F / rc;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    int tile = blockIdx.x;
+    float d_n = 0.f;
+    int own_n = -1, nbr_n = 0, prev_n = -1;
+    auto prefetch = [&](int t) {
+      const int e = t * TILE + tid;
+      d_n = 0.f; own_n = -1; nbr_n = 0; prev_n = -1;
+      if (e < E) {
+        d_n = __ldg(&dist[e]);
+        own_n = __ldg(&edge_owner[e]);
+        nbr_n = __ldg(&edge_nbr[e]);
+        if (e > 0) prev_n = __ldg(&edge_owner[e - 1]);
+      }
+    };
+    float dq[3] = {0.f, 0.f, 0.f}, cq[3] = {0.f, 0.f, 0.f};  // (dist, cut) of tiles i, i-1, i-2
+    auto e4 = [&](int i, float d, float cut) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const int e = (blockIdx.x + i * gridDim.x) * TILE + tid;
+      mbar_wait_guard(bar(C_D4_FULL + s), ph);
+      fence_after_sync();
+      const float dcut = d < rc ? -0.5f * pi_over_rc * __sinf(d * pi_over_rc) : 0.f;
+      const float two_g = 2.0f * gamma;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + 256 + s * 64 + lane_sel + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const float diff = d - sCen[c * 32 + u];
+          const float ex = ex2_approx(g2 * diff * diff);
+          // d/dd [exp(gamma diff^2) C(d)] ; columns k >= R hold exact zeros (zero-padded Wf0)
+          acc = fmaf(__uint_as_float(r[u]), ex * fmaf(two_g * diff, cut, dcut), acc);
+        }
+      }
+      if (kExact) {
+        const float* red = reinterpret_cast<const float*>(smem + BO_RED + s * (4 * TILE * 4));
+        acc += dcut * (red[tid] + red[TILE + tid] + red[2 * TILE + tid] + red[3 * TILE + tid]);
+      }
+      fence_before_sync();
+      mbar_arrive(bar(C_D4_EMPTY + s));
+      if (e < E) g_d[e] = accumulate ? g_d[e] + acc : acc;
+    };
+    if (n_my > 0) prefetch(tile);
+    for (int i = 0; i < n_my; ++i, tile += gridDim.x) {
+      const int s = i & 1, ms = i & (META_STAGES - 1);
+      const uint32_t ph = (i >> 1) & 1, mph = (i / META_STAGES) & 1;
+      const float d = d_n;
+      const int own = own_n, nb = nbr_n, prev = prev_n;
+      if (i + 1 < n_my) prefetch(tile + gridDim.x);
+      const bool valid = own >= 0;
+      const float cut = valid ? cosine_cutoff_fast(d, pi_over_rc, rc) : 0.f;
+      const uint32_t bmask = __ballot_sync(0xffffffffu, valid && tid > 0 && own != prev);
+      mbar_wait_guard(bar(C_META_EMPTY + ms), mph ^ 1);
+      mbar_wait_guard(bar(C_RBF_EMPTY + s), ph ^ 1);
+      reinterpret_cast<uint2*>(smem + BO_META + ms * TILE * 8)[tid] =
+          make_uint2((uint32_t)nb * (uint32_t)NF, __float_as_uint(cut));
+      reinterpret_cast<int*>(smem + BO_OWN + ms * TILE * 4)[tid] = valid ? own : 0;
+      if (lane == 0) reinterpret_cast<uint32_t*>(smem + BO_HEAD + ms * 16)[warp] = bmask;
+      write_rbf_row_fast(smem + BO_RBF + s * (128 * 128), sCen, tid, d, cut, g2);
+      fence_async_smem();
+      mbar_arrive(bar(C_RBF_FULL + s));
+      mbar_arrive(bar(C_META_FULL + ms));
+      dq[2] = dq[1]; dq[1] = dq[0]; dq[0] = d;
+      cq[2] = cq[1]; cq[1] = cq[0]; cq[0] = cut;
+      if (i >= 2) e4(i - 2, dq[2], cq[2]);
+    }
+    if (n_my >= 2) e4(n_my - 2, dq[1], cq[1]);
+    if (n_my >= 1) e4(n_my - 1, dq[0], cq[0]);
+  } else if (warp < 12) {
+    // =========================================================== G0 / G1: gW0^T rows (thread = feature f)
+    const int g = warp < 8 ? 0 : 1;
+    const int f = (warp & 3) * 32 + lane;
+    const float* __restrict__ af = a + f;
+    const float* __restrict__ gmf = g_m + f;
+    for (int i = g; i < n_my; i += 2) {
+      const int ms = i & (META_STAGES - 1);
+      const uint32_t ph = (i >> 1) & 1, mph = (i / META_STAGES) & 1;
+      const uint4* sMeta2 = reinterpret_cast<const uint4*>(smem + BO_META + ms * TILE * 8);
+      const int* sOwn = reinterpret_cast<const int*>(smem + BO_OWN + ms * TILE * 4);
+      const uint32_t* sMask = reinterpret_cast<const uint32_t*>(smem + BO_HEAD + ms * 16);
+      uint8_t* sOp = smem + BO_OP + g * (2 * 128 * 128);
+      mbar_wait_guard(bar(C_META_FULL + ms), mph);
+      float gm = __ldg(gmf + (size_t)sOwn[0] * NF);
+      mbar_wait_guard(bar(C_OP_EMPTY + g), ph ^ 1);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float av[32];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const uint4 m = sMeta2[c * 16 + u];
+          av[2 * u] = __ldg(af + m.x);
+          av[2 * u + 1] = __ldg(af + m.z);
+        }
+        const uint32_t bits = sMask[c];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (((bits >> (8 * q)) & 0xffu) == 0u) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) av[q * 8 + u] *= gm;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if ((bits >> (8 * q + u)) & 1u) gm = __ldg(gmf + (size_t)sOwn[c * 32 + q * 8 + u] * NF);
+              av[q * 8 + u] *= gm;
+            }
+          }
+          const int chunk = c * 4 + q;
+          *reinterpret_cast<uint4*>(sOp + (chunk >> 3) * (128 * 128) + sw128_off(f, chunk & 7)) =
+              make_uint4(pack_half2(av[q * 8], av[q * 8 + 1]), pack_half2(av[q * 8 + 2], av[q * 8 + 3]),
+                         pack_half2(av[q * 8 + 4], av[q * 8 + 5]), pack_half2(av[q * 8 + 6], av[q * 8 + 7]));
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(bar(C_GW_FULL + g));
+      mbar_arrive(bar(C_META_EMPTY + ms));
+    }
+  } else if (warp < 16) {
+    // =========================================================== T (thread = feature j)
+    const int j = (warp & 3) * 32 + lane;
+    const int wq = warp & 3;
+    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
+    const float bias = sBias[j];
+    auto phaseA = [&](int i) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      uint8_t* sT = smem + BO_ST + s * (2 * 128 * 128);
+      mbar_wait_guard(bar(C_D1_FULL + s), ph);
+      fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + s * 128 + lane_sel + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t p[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            p[u] = pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u]) + bias),
+                              tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]) + bias));
+          const int chunk = c * 4 + q;
+          *reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7)) =
+              make_uint4(p[0], p[1], p[2], p[3]);
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(bar(C_D1_EMPTY + s));
+    };
+    auto phaseB = [&](int i) {
+      const int s = i & 1, ms = i & (META_STAGES - 1);
+      const uint32_t ph = (i >> 1) & 1;
+      const uint8_t* sT = smem + BO_ST + s * (2 * 128 * 128);
+      uint8_t* sOp = smem + BO_OP + s * (2 * 128 * 128);
+      const uint4* sMeta2 = reinterpret_cast<const uint4*>(smem + BO_META + ms * TILE * 8);
+      float* red = reinterpret_cast<float*>(smem + BO_RED + s * (4 * TILE * 4));
+      mbar_wait_guard(bar(C_D3_FULL + s), ph);
+      if (kExact) mbar_wait_guard(bar(C_D4_EMPTY + s), ph ^ 1);  // e4(i-2) has read sRed[s]
+      fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + s * 128 + lane_sel + c * 32, r);
+        tmem_ld_wait();
+        float uu[32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = c * 4 + q;
+          const uint4 tq = *reinterpret_cast<const uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7));
+          const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
+          uint32_t p[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = q * 8 + 2 * u;
+            const float2 tt = unpack_h2(tw[u]);
+            const uint4 m = sMeta2[c * 16 + q * 4 + u];  // cuts of edges k, k+1
+            const float d0 = __uint_as_float(r[k]), d1 = __uint_as_float(r[k + 1]);
+            uu[k] = tt.x * d0;
+            uu[k + 1] = tt.y * d1;
+            p[u] = pack_half2(__uint_as_float(m.y) * d0 * fmaf(-tt.x, tt.x, 1.f),
+                              __uint_as_float(m.w) * d1 * fmaf(-tt.y, tt.y, 1.f));
+          }
+          *reinterpret_cast<uint4*>(sOp + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7)) =
+              make_uint4(p[0], p[1], p[2], p[3]);
+        }
+        if (kExact) {
+#pragma unroll
+          for (int w = 16; w >= 1; w >>= 1) {
+            const bool up = (lane & w) != 0;
+#pragma unroll
+            for (int u = 0; u < w; ++u) {
+              const float send = up ? uu[u] : uu[u + w];
+              const float keep = up ? uu[u + w] : uu[u];
+              uu[u] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            }
+          }
+          red[wq * TILE + c * 32 + lane] = uu[0];
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(bar(C_D3_EMPTY + s));
+      fence_async_smem();
+      mbar_arrive(bar(C_GT_FULL + s));
+      mbar_arrive(bar(C_META_EMPTY + ms));
+    };
+    if (n_my > 0) phaseA(0);
+    for (int i = 0; i < n_my; ++i) {
+      if (i + 1 < n_my) phaseA(i + 1);
+      phaseB(i);
+    }
+  } else {
+    // =========================================================== M: MMA issuer
+    if (lane == 0 && n_my > 0) {
+      constexpr uint32_t IDESC1 = idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t IDESC3 = idesc_f16(128, 128, 1, 1);
+      constexpr uint32_t IDESC4 = idesc_f16(128, 64, 1, 1);
+      const uint64_t dA1 = smem_desc_sw128(sbase + BO_WF0, 16, 1024);
+      const uint64_t dA3 = smem_desc_sw128(sbase + BO_WF1, 128 * 128, 1024);  // Wf1 [f][j] read MN-major (M = j)
+      const uint64_t dB4 = smem_desc_sw128(sbase + BO_WF0, 16, 1024);         // Wf0 [j][k] read MN-major (N = k)
+      auto issue1 = [&](int i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait_guard(bar(C_RBF_FULL + s), ph);
+        mbar_wait_guard(bar(C_D3_EMPTY + s), ph ^ 1);  // D13[s] drained by phaseB(i-2)
+        fence_after_sync();
+        const uint64_t dB1 = smem_desc_sw128(sbase + BO_RBF + s * (128 * 128), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < RP / 16; ++k) mma_f16(tmem + s * 128, dA1 + 2 * k, dB1 + 2 * k, IDESC1, k > 0);
+        mma_commit(bar(C_RBF_EMPTY + s));
+        mma_commit(bar(C_D1_FULL + s));
+      };
+      auto issue3 = [&](int i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait_guard(bar(C_GW_FULL + s), ph);
+        mbar_wait_guard(bar(C_D1_EMPTY + s), ph);  // phaseA(i) has drained D1 from D13[s]
+        fence_after_sync();
+        const uint64_t dB3 = smem_desc_sw128(sbase + BO_OP + s * (2 * 128 * 128), 128 * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < NF / 16; ++k)
+          mma_f16(tmem + s * 128, dA3 + (uint64_t)(k * (2048 / 16)), dB3 + (uint64_t)(k * (2048 / 16)), IDESC3, k > 0);
+        mma_commit(bar(C_D3_FULL + s));
+      };
+      auto issue4 = [&](int i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait_guard(bar(C_GT_FULL + s), ph);
+        mbar_wait_guard(bar(C_D4_EMPTY + s), ph ^ 1);
+        fence_after_sync();
+        const uint64_t dA4 = smem_desc_sw128(sbase + BO_OP + s * (2 * 128 * 128), 128 * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < NF / 16; ++k)
+          mma_f16(tmem + 256 + s * 64, dA4 + (uint64_t)(k * (2048 / 16)), dB4 + (uint64_t)(k * (2048 / 16)), IDESC4,
+                  k > 0);
+        mma_commit(bar(C_OP_EMPTY + s));
+        mma_commit(bar(C_D4_FULL + s));
+      };
+      issue1(0);
+      for (int i = 0; i < n_my; ++i) {
+        if (i + 1 < n_my) issue1(i + 1);
+        issue3(i);
+        if (i >= 1) issue4(i - 1);
+      }
+      issue4(n_my - 1);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 
 // defined in fmd_filter_tc.cu
@@ -292,6 +656,32 @@ extern "C" int fmd_filter_cfconv_fwd2(const float* dist, const int32_t* edge_own
     FMD_CHECK_LAUNCH();
   }
   fmd_cfconv_fixup_launch(seg_ptr, n_nodes, capacity, part, out, st);
+  FMD_CHECK_LAUNCH();
+  return FMD_OK;
+}
+
+extern "C" int fmd_filter_cfconv_bwd2(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr,
+                                      int capacity, const int32_t* n_edges_dev, const void* wf0_h, const void* bf0_h,
+                                      const void* wf1_h, const float* centers, int num_rbf, float gamma, float rc,
+                                      const float* a, const float* g_m, int n_feat, float* g_d, int accumulate,
+                                      int exact_cutoff_grad, void* stream) {
+  FMD_REQUIRE(dist && edge_owner && edge_nbr && wf0_h && wf1_h && centers && a && g_m && g_d,
+              "fmd_filter_cfconv_bwd2: null argument");
+  FMD_REQUIRE(n_feat == NF && num_rbf > 0 && num_rbf <= RP, "fmd_filter_cfconv_bwd2: needs F == 128 and num_rbf <= 64");
+  if (capacity <= 0) return FMD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ex = exact_cutoff_grad ? 1 : 0;
+  auto kern = ex ? filter_cfconv_bwd2_kernel<true> : filter_cfconv_bwd2_kernel<false>;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[ex]) {
+    FMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSMEM_ALLOC));
+    attr_done[ex] = true;
+  }
+  const int max_tiles = fmd_div_up(capacity, TILE);
+  const int grid = max_tiles < fmd_num_sms() ? max_tiles : fmd_num_sms();
+  kern<<<grid, NTHREADS, BSMEM_ALLOC, st>>>(dist, edge_owner, edge_nbr, capacity, n_edges_dev, (const __half*)wf0_h,
+                                            (const __half*)bf0_h, (const __half*)wf1_h, centers, num_rbf, gamma, rc, a,
+                                            g_m, g_d, accumulate);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

@@ -51,6 +51,9 @@ _SIGS = {
     "fmd_filter_cfconv_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
                               c_int),
+    "fmd_filter_cfconv_bwd2": ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
+                               c_int),
     "fmd_linear": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                     c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "fmd_embedding": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),

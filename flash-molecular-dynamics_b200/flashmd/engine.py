@@ -279,7 +279,7 @@ class ForceField:
     def _filter_cfconv_bwd(self, l, a, g_m):
         """g_d[e] += d/dd_e of sum_f g_m[src_e,f] W_l(d_e)[f] a[dst_e,f] C(d_e) (fused, tensor cores)."""
         w, k = self.w, self.w.k
-        L.call("fmd_filter_cfconv_bwd", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), self.cap,
+        L.call("fmd_filter_cfconv_bwd2", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), self.cap,
                L.ptr(self.n_edges_dev), L.ptr(k[f"b{l}.f0_w.hp"]), L.ptr(k[f"b{l}.f0_b.h"]), L.ptr(k[f"b{l}.f1_w.h"]),
                L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(a), L.ptr(g_m), w.filters, L.ptr(self.g_d), 1,
                int(self.exact), self._st)

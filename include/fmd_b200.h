@@ -176,6 +176,13 @@ int fmd_filter_cfconv_bwd(const float* dist, const int32_t* edge_owner, const in
                           const float* centers, int num_rbf, float gamma, float rc, const float* a, const float* g_m,
                           int n_feat, float* g_d, int accumulate, int exact_cutoff_grad, void* stream);
 
+/* Same contract as fmd_filter_cfconv_bwd: the warp-specialised, software-pipelined kernel used on the step
+ * path (producer+g_d / gather / tanh+g_t / MMA-issuer warps, mbarrier rings, D1|D3 and D4 double-buffered in TMEM). */
+int fmd_filter_cfconv_bwd2(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr, int capacity,
+                           const int32_t* n_edges_dev, const void* wf0_h, const void* bf0_h, const void* wf1_h,
+                           const float* centers, int num_rbf, float gamma, float rc, const float* a, const float* g_m,
+                           int n_feat, float* g_d, int accumulate, int exact_cutoff_grad, void* stream);
+
 /* ---------------------------------------------------------------- dense layers -------------- */
 
 /* replaces: fused_tanh_linear (kernels/cfconv_kernels.py:1758-1941), fused_linear_tanh_fp16 (:644-760),

@@ -51,6 +51,13 @@ def run(sizes, box, rc, R=50, seed=0, timing=False):
         Cm = C if exact else C.detach()
         loss = (gm[src.long()] * a[dst.long()] * W * Cm[:, None]).sum()
         (ref,) = torch.autograd.grad(loss, d)
+        g_d2 = torch.full((max(E, 1),), float("nan"), device=dev)
+        L.call("fmd_filter_cfconv_bwd2", L.ptr(dist), L.ptr(src), L.ptr(dst), E, None, L.ptr(wf0p), L.ptr(bf0h),
+               L.ptr(wf1h), L.ptr(centers), R, gamma, float(rc), L.ptr(a), L.ptr(gm), F, L.ptr(g_d2), 0, exact,
+               L.stream_ptr())
+        torch.cuda.synchronize()
+        res[f"v2_exact{exact}"] = float((g_d2[:E] - ref).norm() / ref.norm().clamp_min(1e-30))
+        res[f"v2_nan{exact}"] = int(torch.isnan(g_d2[:E]).sum())
         res[f"exact{exact}"] = float((g_d[:E] - ref).norm() / ref.norm().clamp_min(1e-30))
         res[f"nan{exact}"] = int(torch.isnan(g_d[:E]).sum())
     if timing:
@@ -64,6 +71,12 @@ def run(sizes, box, rc, R=50, seed=0, timing=False):
             ("bwd_exact", lambda: L.call("fmd_filter_cfconv_bwd", L.ptr(dist), L.ptr(src), L.ptr(dst), E, None,
                                          L.ptr(wf0p), L.ptr(bf0h), L.ptr(wf1h), L.ptr(centers), R, gamma, float(rc),
                                          L.ptr(a), L.ptr(gm), F, L.ptr(g_d), 1, 1, L.stream_ptr())),
+            ("bwd2_exact", lambda: L.call("fmd_filter_cfconv_bwd2", L.ptr(dist), L.ptr(src), L.ptr(dst), E, None,
+                                          L.ptr(wf0p), L.ptr(bf0h), L.ptr(wf1h), L.ptr(centers), R, gamma, float(rc),
+                                          L.ptr(a), L.ptr(gm), F, L.ptr(g_d), 1, 1, L.stream_ptr())),
+            ("bwd2_compat", lambda: L.call("fmd_filter_cfconv_bwd2", L.ptr(dist), L.ptr(src), L.ptr(dst), E, None,
+                                           L.ptr(wf0p), L.ptr(bf0h), L.ptr(wf1h), L.ptr(centers), R, gamma, float(rc),
+                                           L.ptr(a), L.ptr(gm), F, L.ptr(g_d), 1, 0, L.stream_ptr())),
             ("bwd_compat", lambda: L.call("fmd_filter_cfconv_bwd", L.ptr(dist), L.ptr(src), L.ptr(dst), E, None,
                                           L.ptr(wf0p), L.ptr(bf0h), L.ptr(wf1h), L.ptr(centers), R, gamma, float(rc),
                                           L.ptr(a), L.ptr(gm), F, L.ptr(g_d), 1, 0, L.stream_ptr()))):
