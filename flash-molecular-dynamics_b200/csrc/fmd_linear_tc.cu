@@ -1,0 +1,266 @@
+// Node-level dense layers on the sm_100a tensor cores (tcgen05.mma kind::tf32, fp32 TMEM accumulator):
+//   Y[M,N] = epi( pro(X)[M,K] @ W[K,N] + bias ) [* (1 - aux^2)] [+ res]        K, N in {32..128}
+// Same contract as fmd_linear; TF32 operands are what the reference's GPU path uses for these layers
+// (nn.Linear under torch.set_float32_matmul_precision("high"), scripts/nvt_langevin.py:38; tl.dot default
+// in fused_tanh_linear, kernels/cfconv_kernels.py:1758-1843).  fp16 inputs are exact in TF32, so the
+// W16A16 output network (fp16 operands, fp32 accumulate: models/gptq.py:266-306) is reproduced exactly.
+// The fp32 parity path (1e-5) never comes here: it stays on the true-fp32 FMA kernel of fmd_linear.cu.
+//
+// One persistent CTA per SM, 128 threads.  The weight matrix is staged once per CTA (transposed on the
+// fly into the K-major B operand); per 128-row tile the CTA stages pro(X) as the K-major A operand (round-to-nearest TF32),
+// one thread issues K/8 MMAs (both operands K-major), and thread r drains row r of the accumulator through the epilogue.
+#include "fmd_tc.cuh"
+
+using namespace fmd;
+using namespace fmd::tc;
+
+namespace {
+
+constexpr int LT_TILE = 128;
+constexpr uint32_t LO_A = 0;                  // up to 4 K-blocks x [128 rows][128 B] = 64 KB
+constexpr uint32_t LO_B = 64 * 1024;          // up to 4 N-blocks x [128 k][128 B]   = 64 KB
+constexpr uint32_t LO_BIAS = 128 * 1024;      // 128 floats
+constexpr uint32_t LO_BAR = LO_BIAS + 512;
+constexpr uint32_t LT_SMEM = LO_BAR + 32;
+constexpr uint32_t LT_SMEM_ALLOC = LT_SMEM + 1024;
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// round-to-nearest (ties away) to TF32 with two full-rate integer ops (cvt.rna.tf32.f32 is a slow-pipe
+// instruction and was the top stall of this kernel); identical for finite inputs
+__device__ __forceinline__ float to_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float act(float v, int a) {
+  if (a == FMD_ACT_TANH) return tanhf(v);
+  if (a == FMD_ACT_TANH_CLAMPED) return tanh_clamped(v);
+  return v;
+}
+
+template <typename TX>
+__device__ __forceinline__ float4 load_x4(const TX* p);
+template <>
+__device__ __forceinline__ float4 load_x4<float>(const float* p) { return load4(p); }
+template <>
+__device__ __forceinline__ float4 load_x4<__half>(const __half* p) { return load4(p); }
+
+template <typename TX, typename TW, typename TY>
+__global__ void __launch_bounds__(LT_TILE, 1)
+linear_tc_kernel(const TX* __restrict__ X, const TW* __restrict__ W, const TW* __restrict__ bias, TY* __restrict__ Y,
+                 int M, int N, int K, const int32_t* __restrict__ m_dev, int pro_act, int x_round_f16, int epi_act,
+                 const void* __restrict__ aux, int auxdt, const float* __restrict__ res, int w_nk) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* sBias = reinterpret_cast<float*>(smem + LO_BIAS);
+  const uint32_t bar = sbase + LO_BAR;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + LO_BAR + 16);
+  if (m_dev) M = min(M, *m_dev);
+  const int n_tiles = (M + LT_TILE - 1) / LT_TILE;
+  const int kc = K / 4;  // 16-byte chunks per X row
+
+  // ---- weights -> K-major B operand [N rows][K], K-block kb (32 floats) at kb * N * 128 bytes
+  if (w_nk) {
+    // W given as [N][K] (nn.Linear.weight layout): 16-byte chunks, coalesced, 8 in flight
+    const int kc_shift = (K == 128) ? 5 : 4;
+    const int total = N << kc_shift;
+    for (int base = 0; base < total; base += LT_TILE * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * LT_TILE + tid;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < total) v[u] = load4(W + (size_t)idx * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * LT_TILE + tid;
+        const int n = idx >> kc_shift, c = idx & (kc - 1);
+        float4 t = v[u];
+        t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
+        if (idx < total) *reinterpret_cast<float4*>(smem + LO_B + (c >> 3) * (N * 128) + sw128_off(n, c & 7)) = t;
+      }
+    }
+  } else {
+    // W given as [K][N]: task = (n, 4 consecutive k), the scalar loads are coalesced across threads (n fastest)
+    const int n_shift = (N == 128) ? 7 : 6;
+    const int total = (K >> 2) * N;
+    for (int base = 0; base < total; base += LT_TILE * 4) {
+      float w[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * LT_TILE + tid;
+        const int n = idx & (N - 1), kq = idx >> n_shift;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[u][q] = idx < total ? to_f32<TW>(W[(size_t)(kq * 4 + q) * N + n]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * LT_TILE + tid;
+        const int n = idx & (N - 1), kq = idx >> n_shift;
+        if (idx < total)
+          *reinterpret_cast<float4*>(smem + LO_B + (kq >> 3) * (N * 128) + sw128_off(n, kq & 7)) =
+              make_float4(to_tf32(w[u][0]), to_tf32(w[u][1]), to_tf32(w[u][2]), to_tf32(w[u][3]));
+      }
+    }
+  }
+  if (tid < N) sBias[tid] = bias ? to_f32<TW>(bias[tid]) : 0.f;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(sbase + LO_BAR + 16, 128);
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint32_t idesc = idesc_tf32(128, N, 0, 0);
+  const uint64_t dA = smem_desc_sw128(sbase + LO_A, 16, 1024);
+  const uint64_t dB = smem_desc_sw128(sbase + LO_B, 16, 1024);
+  const uint32_t b_kblock = (uint32_t)(N * 128 / 16);
+
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int m0 = tile * LT_TILE;
+    // ---- stage pro(X) tile: [128 rows][K] fp32, K-block kb (32 floats) at kb * 16 KB; 8 loads in flight per thread
+    {
+      const int kc_shift = (K == 128) ? 5 : 4;
+      const int total = LT_TILE << kc_shift;
+      for (int base = 0; base < total; base += LT_TILE * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = base + u * LT_TILE + tid;
+          const int r = idx >> kc_shift, c = idx & (kc - 1);
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0 + r < M) v[u] = load_x4<TX>(X + (size_t)(m0 + r) * K + c * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = base + u * LT_TILE + tid;
+          const int r = idx >> kc_shift, c = idx & (kc - 1);
+          float4 t = v[u];
+          if (x_round_f16) {
+            t.x = __half2float(__float2half_rn(t.x)); t.y = __half2float(__float2half_rn(t.y));
+            t.z = __half2float(__float2half_rn(t.z)); t.w = __half2float(__float2half_rn(t.w));
+          }
+          if (pro_act) { t.x = act(t.x, pro_act); t.y = act(t.y, pro_act); t.z = act(t.z, pro_act); t.w = act(t.w, pro_act); }
+          t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
+          *reinterpret_cast<float4*>(smem + LO_A + (c >> 3) * (128 * 128) + sw128_off(r, c & 7)) = t;
+        }
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();  // previous tile's accumulator reads are complete
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      for (int k = 0; k < K / 8; ++k)
+        mma_tf32(tmem, dA + (uint64_t)((k >> 2) * (128 * 128 / 16) + (k & 3) * 2), dB + (uint64_t)((k >> 2) * b_kblock + (k & 3) * 2), idesc,
+                 k > 0);
+      mma_commit(bar);
+    }
+    mbar_wait(bar, it & 1u);
+    fence_after_sync();
+    // ---- epilogue: thread r owns output row m0 + r
+    const int m = m0 + tid;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t rr[32];
+      tmem_ld32(tmem + lane_sel + c0, rr);
+      tmem_ld_wait();
+      if (m < M) {
+        const size_t o = (size_t)m * N + c0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(rr[q * 4 + u]) + sBias[c0 + q * 4 + u];
+          if (epi_act) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = act(v[u], epi_act);
+          }
+          if (aux) {
+            float4 t;
+            if (auxdt == FMD_F16) t = load4(reinterpret_cast<const __half*>(aux) + o + q * 4);
+            else t = load4(reinterpret_cast<const float*>(aux) + o + q * 4);
+            v[0] *= 1.f - t.x * t.x; v[1] *= 1.f - t.y * t.y; v[2] *= 1.f - t.z * t.z; v[3] *= 1.f - t.w * t.w;
+          }
+          if (res) {
+            const float4 t = load4(res + o + q * 4);
+            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+          }
+          store4(Y + o + q * 4, make_float4(v[0], v[1], v[2], v[3]));
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <typename TX, typename TW, typename TY>
+int launch_tc(const void* X, const void* W, const void* bias, void* Y, int M, int N, int K, const int32_t* m_dev,
+              int pro_act, int x_round, int epi_act, const void* aux, int auxdt, const float* res, int w_nk, cudaStream_t st) {
+  auto kern = linear_tc_kernel<TX, TW, TY>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM_ALLOC));
+    attr_done = true;
+  }
+  const int tiles = fmd_div_up(M, LT_TILE);
+  const int grid = tiles < fmd_num_sms() ? tiles : fmd_num_sms();
+  kern<<<grid, LT_TILE, LT_SMEM_ALLOC, st>>>((const TX*)X, (const TW*)W, (const TW*)bias, (TY*)Y, M, N, K, m_dev,
+                                             pro_act, x_round, epi_act, aux, auxdt, res, w_nk);
+  return FMD_OK;
+}
+
+}  // namespace
+
+extern "C" int fmd_linear_tc(const void* X, int xdt, const void* W, int wdt, const void* bias, void* Y, int ydt, int M,
+                             int N, int K, const int32_t* m_dev, int pro_act, int x_round_f16, int epi_act,
+                             const void* aux, int auxdt, const float* res, int w_is_nk, void* stream) {
+  FMD_REQUIRE(X && W && Y && M >= 0, "fmd_linear_tc: bad arguments");
+  FMD_REQUIRE((K == 64 || K == 128) && (N == 64 || N == 128),
+              "fmd_linear_tc: needs K, N in {64, 128} (use fmd_linear otherwise)");
+  FMD_REQUIRE((xdt | wdt | ydt | auxdt) >= 0 && xdt <= 1 && wdt <= 1 && ydt <= 1 && auxdt <= 1, "fmd_linear_tc: bad dtype");
+  if (M == 0) return FMD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int key = xdt * 4 + wdt * 2 + ydt;
+  int rc = FMD_OK;
+#define FMD_LT(TX, TW, TY) \
+  rc = launch_tc<TX, TW, TY>(X, W, bias, Y, M, N, K, m_dev, pro_act, x_round_f16, epi_act, aux, auxdt, res, w_is_nk, st)
+  switch (key) {
+    case 0: FMD_LT(float, float, float); break;
+    case 1: FMD_LT(float, float, __half); break;
+    case 2: FMD_LT(float, __half, float); break;
+    case 3: FMD_LT(float, __half, __half); break;
+    case 4: FMD_LT(__half, float, float); break;
+    case 5: FMD_LT(__half, float, __half); break;
+    case 6: FMD_LT(__half, __half, float); break;
+    case 7: FMD_LT(__half, __half, __half); break;
+    default: FMD_FAIL("fmd_linear_tc: bad dtype combination");
+  }
+#undef FMD_LT
+  if (rc != FMD_OK) return rc;
+  FMD_CHECK_LAUNCH();
+  return FMD_OK;
+}

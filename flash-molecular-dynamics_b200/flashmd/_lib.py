@@ -56,6 +56,8 @@ _SIGS = {
                                c_int),
     "fmd_linear": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                     c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p], c_int),
+    "fmd_linear_tc": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                       c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
     "fmd_embedding": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
     "fmd_segment_sum": ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
     "fmd_prior_energy_forces": ([c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,

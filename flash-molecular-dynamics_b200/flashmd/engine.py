@@ -82,6 +82,13 @@ class SchNetWeights:
                 wp[:, :self.num_rbf] = k[f"b{l}.f0_w.h"]
                 k[f"b{l}.f0_w.hp"] = wp.contiguous()
         self.k = k
+        # [K,N] weight tensor -> the same matrix stored [N,K] (its transpose twin), for fmd_linear_tc's fast staging
+        self.twin = {}
+        for name in list(k.keys()):
+            base = name.replace("_wT", "_w")
+            if "_wT" in name and base in k:
+                self.twin[k[name].data_ptr()] = k[base]
+                self.twin[k[base].data_ptr()] = k[name]
         self.ones_col = None
 
     @staticmethod
@@ -256,10 +263,17 @@ class ForceField:
     def _lin(self, x, w, bias, y, m_dev=None, **kw):
         M, K = x.shape
         N = w.shape[1]
-        L.call("fmd_linear", L.ptr(x), L.dt_code(x), L.ptr(w), L.dt_code(w), L.ptr(bias), L.ptr(y), L.dt_code(y), M, N,
-               K, L.ptr(m_dev), kw.get("pro_act", 0), int(kw.get("x_round", False)), kw.get("epi_act", 0),
-               L.ptr(kw.get("aux")), L.dt_code(kw["aux"]) if kw.get("aux") is not None else 0, L.ptr(kw.get("res")),
-               self._st)
+        tc = self.fused_tc and K in (64, 128) and N in (64, 128)
+        args = (L.ptr(x), L.dt_code(x), L.ptr(w), L.dt_code(w), L.ptr(bias), L.ptr(y), L.dt_code(y), M, N,
+                K, L.ptr(m_dev), kw.get("pro_act", 0), int(kw.get("x_round", False)), kw.get("epi_act", 0),
+                L.ptr(kw.get("aux")), L.dt_code(kw["aux"]) if kw.get("aux") is not None else 0, L.ptr(kw.get("res")))
+        if tc:
+            wt = self.w.twin.get(w.data_ptr())
+            if wt is not None:
+                args = args[:2] + (L.ptr(wt),) + args[3:]
+            L.call("fmd_linear_tc", *args, int(wt is not None), self._st)
+        else:
+            L.call("fmd_linear", *args, self._st)
         self._n += 1
 
     def _cfconv(self, x, W, out):

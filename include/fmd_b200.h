@@ -197,6 +197,17 @@ int fmd_linear(const void* X, int xdt, const void* W, int wdt, const void* bias,
                int N, int K, const int32_t* m_dev, int pro_act, int x_round_f16, int epi_act,
                const void* aux, int auxdt, const float* res, void* stream);
 
+/* Same contract as fmd_linear for K, N in {64, 128}, computed on the tensor cores (tcgen05.mma
+ * kind::tf32, fp32 accumulate in TMEM): operands are rounded to TF32 (round-to-nearest), which is what the
+ * reference's GPU path does for these layers (nn.Linear under set_float32_matmul_precision("high"),
+ * scripts/nvt_langevin.py:38; tl.dot default in fused_tanh_linear kernels/cfconv_kernels.py:1758-1843);
+ * fp16 operands are exact. Used by the W16A16 step for the node-level layers; the fp32 parity path
+ * keeps fmd_linear. w_is_nk != 0: W is given as [N,K] (the nn.Linear.weight layout) instead of [K,N],
+ * which lets the kernel stage it with 16-byte loads. */
+int fmd_linear_tc(const void* X, int xdt, const void* W, int wdt, const void* bias, void* Y, int ydt, int M, int N,
+                  int K, const int32_t* m_dev, int pro_act, int x_round_f16, int epi_act, const void* aux, int auxdt,
+                  const float* res, int w_is_nk, void* stream);
+
 /* ---------------------------------------------------------------- node-level helpers -------- */
 
 /* replaces: torch.nn.Embedding (models/schnet.py:203). out[i,:] = table[types[i],:]. types: idx_bytes. */

@@ -195,6 +195,52 @@ def test_dense_layers(M, K, N):
 
 
 # ----------------------------------------------------------------------------- whole force field
+@pytest.mark.parametrize("M,K,N", [(1000, 128, 128), (34432, 128, 128), (777, 64, 128), (300, 128, 64), (5, 64, 64)])
+def test_dense_layers_tensor_core_tf32(M, K, N):
+    """fmd_linear_tc (tcgen05 kind::tf32) against torch fp64 on TF32-rounded operands (tight) and on the
+    raw fp32 operands (TF32 rounding level), with every epilogue; fp16 operands are exact."""
+    from flashmd import _lib as L
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn((M, K), generator=g).to(DEV)
+    w = (torch.randn((K, N), generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    aux = torch.tanh(torch.randn((M, N), generator=g)).to(DEV)
+    res = torch.randn((M, N), generator=g).to(DEV)
+
+    def tf32(t):  # round-to-nearest (ties away) to 10 mantissa bits
+        i = t.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    def run(x_, w_, b_, ydt, **kw):
+        ys = []
+        for nk in (0, 1):   # W given as [K,N], then the same matrix given as [N,K]
+            wv = w_.t().contiguous() if nk else w_
+            y = torch.empty((M, N), dtype=ydt, device=DEV)
+            L.call("fmd_linear_tc", L.ptr(x_), L.dt_code(x_), L.ptr(wv), L.dt_code(wv), L.ptr(b_), L.ptr(y), L.dt_code(y),
+                   M, N, K, None, kw.get("pro", 0), int(kw.get("xr", False)), kw.get("epi", 0), L.ptr(kw.get("aux")),
+                   L.dt_code(kw["aux"]) if kw.get("aux") is not None else 0, L.ptr(kw.get("res")), nk, L.stream_ptr())
+            ys.append(y)
+        assert torch.equal(ys[0], ys[1])
+        return ys[0]
+    y = run(x, w, b, torch.float32)
+    ref_t = tf32(x).double() @ tf32(w).double() + b.double()
+    assert rel_l2(y.cpu(), ref_t.cpu()) < 2e-6
+    assert rel_l2(y.cpu(), (x.double() @ w.double() + b.double()).cpu()) < 2e-3
+    y = run(x, w, b, torch.float32, epi=L.ACT_TANH, aux=aux, res=res)
+    ref = torch.tanh(ref_t) * (1 - aux.double() ** 2) + res.double()
+    assert rel_l2(y.cpu(), ref.cpu()) < 5e-6
+    y = run(x, w, None, torch.float32, pro=L.ACT_TANH)
+    ref = tf32(torch.tanh(x)).double() @ tf32(w).double()
+    assert rel_l2(y.cpu(), ref.cpu()) < 5e-6
+    # fp16 operands (exact in TF32), fp16 output, the reference's clamped tanh
+    xh, wh, bh = x.half(), w.half(), b.half()
+    y = run(x, wh, bh, torch.float16, xr=True, epi=L.ACT_TANH_CLAMPED)
+    ref = torch.tanh(xh.double() @ wh.double() + bh.double())
+    assert rel_l2(y.float().cpu(), ref.cpu()) < 1e-3
+    y = run(xh, wh, None, torch.float32)
+    assert rel_l2(y.cpu(), (xh.double() @ wh.double()).cpu()) < 2e-6
+
+
 @pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz"])
 def test_schnet_fp32_vs_reference_golden(name):
     """fp32 energies and forces within 1e-5 relative of the reference's fp32 path (north star)."""
