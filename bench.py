@@ -46,11 +46,13 @@ def parse():
 
 
 def peaks():
+    """(hbm GB/s, bf16 TF/s sustained, bf16 TF/s burst, source) - measured on this pool's B200s by the driver."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return (float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), float(d["bf16_tflops"]),
+                "measured (MEASURED_PEAKS.json)")
+    return 6650.0, 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -189,8 +191,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_mols, per_step = 4, 1
-    steps, warm = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    n_mols, per_step = 16, 1
+    steps, warm = max(1, min(args.steps, 20)), max(0, min(args.warmup, 2))
     if warm:
         cpu_oracle_throughput(args, n_mols, warm, cores)
     val, secs = cpu_oracle_throughput(args, n_mols, steps * per_step, cores)
@@ -213,7 +215,8 @@ def workload_config(args, world):
                         f"dt={DT}; priors: bonds+angles+dihedrals+repulsion",
             "n_beads": args.n_beads, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
             "precision_path": args.precision, "parallelism": f"replica-sharded x{world} (no data-path collective)",
-            "l2": "per-step working set (edge tensors, >1 GB) exceeds the 126 MB L2; no explicit flush"}
+            "l2": "inputs larger than L2: one step streams ~0.5 GB of distinct buffers (node activations of all blocks, "
+                  "edge list, prior incidence lists) against a 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -320,7 +323,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 filter tensors / f32 accumulate" if args.precision == "w16a16" else "f32",
+            "dtype": "f16 filter-network operands / tf32 node layers / f32 accumulate" if args.precision == "w16a16" else "f32",
             "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -331,27 +334,30 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            nm = 2
-            val, secs = cpu_oracle_throughput(args, nm, 2, cores)
+            nm, ns = 16, 24
+            cpu_oracle_throughput(args, nm, 1, cores)     # warm-up (thread pool, allocator)
+            val, secs = cpu_oracle_throughput(args, nm, ns, cores)
             line["cpu_baseline"] = {
                 "value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{nm} molecules x {n} beads, 2 BAOAB steps ({secs:.1f} s), oracle port of the reference's "
-                          f"--disable_optim fp32 PyTorch path, {cores} threads"}
+                "sample": f"{nm} molecules x {n} beads, {ns} BAOAB steps ({secs:.1f} s), oracle port of the reference's "
+                          f"--disable_optim fp32 PyTorch path (oracle/fmd_oracle.py), {cores} threads"}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
 
 def kernel_roofline(ff, eng, args, E):
-    """Per-kernel-class device time of one eager step (CUDA events on the launching stream, 3 reps),
-    and the roofline entry of the dominant kernel.  Algorithmic bytes per launch:
-    CFConv CSR: E*F*b (filter) + 4*N*F (x, once) + 4*N*F (out) + 4*E (dst idx) + 4*E (dist) + 4*(N+1)."""
+    """Per-kernel-class device time of one eager step (CUDA events on the launching stream, 3 reps), and the
+    roofline entry of the dominant kernel.  Algorithmic work per launch (DESIGN.md "Kernels"):
+      fused filter-network x CFConv forward (tensor-bound): 2*E*F*(R+F) flop, R = 50 (unpadded);
+      fused backward: 2*E*F*(F+R) flop for g_t = g_W Wf1, g_rbf = g_t Wf0 (the recomputation of t is NOT counted);
+      materialised CFConv CSR (HBM-bound, fp32 path): E*F*b + 8*N*F + 8*E + 4*(N+1) bytes."""
     from flashmd import _lib as L
-    peak, which = peaks()
-    N, F = ff.N, ff.w.filters
+    hbm, tf_sus, tf_burst, which = peaks()
+    N, F, R = ff.N, ff.w.filters, ff.w.num_rbf
     b = 2 if args.precision == "w16a16" else 4
     timings = {}
-    lib = L.load()
+    L.load()
     orig_call = L.call
 
     def timed_call(name, *a):
@@ -374,20 +380,43 @@ def kernel_roofline(ff, eng, args, E):
     for name, evs in timings.items():
         tot = sum(a.elapsed_time(bb) for a, bb in evs)
         table[name] = {"ms_per_step": tot / reps, "launches_per_step": len(evs) // reps}
-    cf = timings.get("fmd_cfconv_csr", [])
-    cf_ms = (sum(a.elapsed_time(bb) for a, bb in cf) / len(cf)) if cf else float("nan")
-    alg = E * F * b + 4 * N * F + 4 * N * F + 4 * E + 4 * E + 4 * (N + 1)
-    achieved = alg / (cf_ms * 1e-3) / 1e9
-    roof = {"kernel": "cfconv_csr_kernel (fmd_cfconv_csr)", "bound": "hbm", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
-            "avg_launch_ms": cf_ms, "launches_per_step": len(cf) // reps, "peak_source": which,
-            "how": "CUDA events around each launch of an eager (non-graph) step, same stream, averaged over 3 steps"}
+
+    def avg_ms(name):
+        ev = timings.get(name, [])
+        return (sum(a.elapsed_time(bb) for a, bb in ev) / len(ev)) if ev else float("nan")
+
+    traffic = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            roof["traffic"] = json.load(open(tp)).get("cfconv_csr_kernel")
+            traffic = json.load(open(tp))
         except Exception:
-            pass
+            traffic = {}
+    how = "CUDA events around each launch of an eager (non-graph) step, same stream, averaged over 3 steps"
+    if "fmd_filter_cfconv_fwd2" in timings:
+        def tensor_roof(cname, kname, flops):
+            ms = avg_ms(cname)
+            ach = flops / (ms * 1e-3) / 1e12
+            return {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
+                    "frac": ach / tf_sus, "traffic": traffic.get(kname), "algorithmic_flops_per_launch": flops,
+                    "avg_launch_ms": ms, "launches_per_step": len(timings[cname]) // reps,
+                    "peak_source": which + " bf16_tflops_sustained (kernel timed inside a long step); burst " +
+                                   f"{tf_burst:.0f}",
+                    "how": how}
+        flops = 2.0 * E * F * (R + F)
+        roof = tensor_roof("fmd_filter_cfconv_fwd2", "filter_cfconv_fwd2_kernel", flops)
+        roof["also"] = [tensor_roof("fmd_filter_cfconv_bwd2", "filter_cfconv_bwd2_kernel", flops)]
+        roof["note"] = ("fp16 tcgen05 GEMMs fused with the tanh / gather / segment-reduce epilogues; the kernel is "
+                        "bound by the SIMT epilogue (MUFU + issue slots), not by the tensor pipe: see DESIGN.md")
+    else:
+        cf_ms = avg_ms("fmd_cfconv_csr")
+        alg = E * F * b + 4 * N * F + 4 * N * F + 4 * E + 4 * E + 4 * (N + 1)
+        achieved = alg / (cf_ms * 1e-3) / 1e9
+        roof = {"kernel": "cfconv_csr_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "frac": achieved / hbm, "traffic": traffic.get("cfconv_csr_kernel"),
+                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": cf_ms,
+                "launches_per_step": len(timings.get("fmd_cfconv_csr", [])) // reps,
+                "peak_source": which + " hbm_gbs (burst copy)", "how": how}
     return roof, table
 
 

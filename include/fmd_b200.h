@@ -96,14 +96,16 @@ int fmd_rbf_bwd(const float* dist, const float* grad_rbf, const float* grad_dist
                 const int32_t* n_edges_dev, const float* centers, int num_rbf, float gamma, float rc,
                 float* g_d, int accumulate, void* stream);
 
-/* second half, generic edge lists (atomic adds, like the reference's index_add_):
+/* replaces: FusedDistanceGaussianRBFCutoffFunction.backward (kernels/cfconv_kernels.py:1696-1733),
+ * second half, generic edge lists (atomic adds, like the reference's index_add_):
  * grad_pos[dst] += g_d * u, grad_pos[src] -= g_d * u, u = (pos[dst]-pos[src]) / max(d, 1e-8).
  * grad_pos [n_nodes,3] must be zero-initialised by the caller. */
 int fmd_edge_grad_to_pos_atomic(const float* pos, const void* edge_src, const void* edge_dst, int idx_bytes,
                                 const float* dist, const float* g_d, int n_edges,
                                 const int32_t* n_edges_dev, float* grad_pos, void* stream);
 
-/* second half, deterministic/atomic-free for the sorted symmetric list of fmd_nl_fill:
+/* replaces: the same second half (kernels/cfconv_kernels.py:1696-1733), deterministic / atomic-free for the
+ * sorted symmetric list of fmd_nl_fill:
  * out[i] = sign * sum_{e in seg(i)} (g_d[e] + g_d[rev[e]]) * u_e    (sign=+1 gives FORCES -dE/dx).
  * accumulate != 0 adds into out. int32 indices. */
 int fmd_edge_grad_to_forces_csr(const float* pos, const int32_t* seg_ptr, const int32_t* edge_dst,
