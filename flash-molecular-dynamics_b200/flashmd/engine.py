@@ -427,7 +427,8 @@ class LangevinEngine:
     as a CUDA graph.  State (pos, vel, forces) lives in fixed device buffers."""
 
     def __init__(self, ff: ForceField, pos: torch.Tensor, vel: torch.Tensor, masses: torch.Tensor,
-                 beta: torch.Tensor, dt: float, friction: float, seed: int = 0, use_graph: bool = True):
+                 beta: torch.Tensor, dt: float, friction: float, seed: int = 0, use_graph: bool = True,
+                 noise_mode: str = "philox"):
         self.ff = ff
         dev = ff.device
         self.pos = pos.detach().to(dev).float().contiguous().clone()
@@ -448,12 +449,18 @@ class LangevinEngine:
         self.ke = torch.zeros(ff.B, dtype=torch.float32, device=dev)
         self.use_graph = use_graph
         self.graph = None
+        # "philox": counter-based noise generated inside the kernel; "buffer": N(0,1) numbers the caller writes
+        # into `noise_buf` before every step (e.g. torch's generator, for step-exact reference comparisons)
+        assert noise_mode in ("philox", "buffer")
+        self.noise_buf = torch.zeros((ff.N, 3), dtype=torch.float32, device=dev) if noise_mode == "buffer" else None
         self.n_steps_done = 0
         self.launches_per_step = 0
         ff.compute(self.pos)   # initial forces (reference simulation/base.py:525-526)
 
     def _step_body(self, noise=None):
         ff, st = self.ff, L.stream_ptr()
+        if noise is None:
+            noise = self.noise_buf
         L.call("fmd_baoab_pre", L.ptr(self.pos), L.ptr(self.vel), L.ptr(ff.forces), L.ptr(self.inv_mass),
                L.ptr(self.noise_std), L.ptr(noise), self.seed, 0, L.ptr(self.step_dev), ff.N, self.dt, self.vscale,
                self.noisescale, st)

@@ -61,3 +61,33 @@ def radius_graph(x: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None
         ptr[1:] = torch.cumsum(counts, 0)
     ei = radius_graph_csr(x, ptr, r, max_num_neighbors)["edge_index"]
     return ei if flow == "target_to_source" else ei.flip(0)
+
+
+def _radius_graph_torch(pos: torch.Tensor, ptr: torch.Tensor, rcut: float, max_num_neighbors: int) -> torch.Tensor:
+    """Plain-PyTorch radius graph with the same semantics / order (the CPU `--disable_optim` path)."""
+    out = []
+    r2 = torch.tensor(float(rcut), dtype=torch.float32) ** 2
+    for b in range(ptr.numel() - 1):
+        lo, hi = int(ptr[b]), int(ptr[b + 1])
+        x = pos[lo:hi].float()
+        d = x[:, None, :] - x[None, :, :]
+        d2 = d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]
+        hit = d2 < r2
+        if max_num_neighbors + 1 < hi - lo:
+            keep = torch.cumsum(hit.to(torch.int32), dim=1) <= max_num_neighbors + 1
+            hit = hit & keep
+        hit.fill_diagonal_(False)
+        ij = hit.nonzero().t()
+        out.append(ij + lo)
+    return torch.cat(out, dim=1) if out else torch.zeros((2, 0), dtype=torch.long)
+
+
+def torch_neighbor_list(data, rcut: float, self_interaction: bool = False, max_num_neighbors: int = 1000) -> torch.Tensor:
+    """edge_index [2,E] of a collated batch (reference torch_impl.py:175-226, no-PBC branch)."""
+    if self_interaction:
+        raise NotImplementedError("self_interaction=True is not supported (the reference never passes it)")
+    pos = data.pos
+    ptr = data["ptr"] if "ptr" in data else torch.tensor([0, pos.shape[0]], device=pos.device)
+    if pos.is_cuda:
+        return radius_graph_csr(pos, ptr, rcut, max_num_neighbors)["edge_index"]
+    return _radius_graph_torch(pos, ptr, rcut, max_num_neighbors)

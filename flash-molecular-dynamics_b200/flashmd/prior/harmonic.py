@@ -1,0 +1,78 @@
+"""k (x - x0)^2 priors on distances and cos(angle) (reference prior/harmonic.py:23-330)."""
+from typing import Dict
+
+import torch
+
+from ..geometry import compute_angles_cos, compute_distances, compute_torsions
+from .base import _Prior, type_table
+
+
+class Harmonic(_Prior):
+    def __init__(self, statistics: Dict, name: str, order: int) -> None:
+        super().__init__()
+        self.allowed_interaction_keys = list(statistics.keys())
+        self.name = name
+        self.order = order
+        self.register_buffer("x_0", type_table(statistics, order, "x_0"))
+        self.register_buffer("k", type_table(statistics, order, "k"))
+
+    def data2parameters(self, data) -> Dict:
+        tt = self.types_of_terms(data)
+        return {"x0": self.x_0[tt], "k": self.k[tt]}
+
+    @staticmethod
+    def compute(x, x0, k, V0=0):
+        return k * (x - x0) ** 2 + V0
+
+    def term_energies(self, data):
+        p = self.data2parameters(data)
+        return Harmonic.compute(self.data2features(data), p["x0"], p["k"])
+
+
+class HarmonicBonds(Harmonic):
+    name = "bonds"
+    kernel_kind = 0
+
+    def __init__(self, statistics) -> None:
+        super().__init__(statistics, HarmonicBonds.name, order=2)
+
+    @staticmethod
+    def compute_features(pos, mapping):
+        return compute_distances(pos, mapping)
+
+    @staticmethod
+    def neighbor_list(topology) -> Dict:
+        return _Prior._nl(HarmonicBonds.name, 2, topology)
+
+
+class HarmonicAngles(Harmonic):
+    """Harmonic in cos(theta)."""
+    name = "angles"
+    kernel_kind = 1
+
+    def __init__(self, statistics) -> None:
+        super().__init__(statistics, HarmonicAngles.name, order=3)
+
+    @staticmethod
+    def compute_features(pos, mapping):
+        return compute_angles_cos(pos, mapping)
+
+    @staticmethod
+    def neighbor_list(topology) -> Dict:
+        return _Prior._nl(HarmonicAngles.name, 3, topology)
+
+
+class HarmonicImpropers(Harmonic):
+    name = "impropers"
+    _order = 4
+
+    def __init__(self, statistics) -> None:
+        super().__init__(statistics, HarmonicImpropers.name, order=4)
+
+    @staticmethod
+    def compute_features(pos, mapping):
+        return compute_torsions(pos, mapping)
+
+    @staticmethod
+    def neighbor_list(topology) -> Dict:
+        return _Prior._nl(HarmonicImpropers.name, 4, topology)

@@ -1,0 +1,163 @@
+"""The drop-in `flashmd` package on CPU (module path = the reference's `--disable_optim` semantics) against
+the golden vectors produced by the UNMODIFIED reference with the same constructor calls
+(oracle/make_golden.py).  These read like the reference's own usage: build StandardSchNet + priors,
+SumOut/GradientsOut, LangevinSimulation / PTSimulation, attach, simulate, read the .npy files."""
+import os
+from copy import deepcopy
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import dropin_model_from_golden, load_golden, rel_l2
+
+
+@pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz"])
+def test_model_objects_match_reference_energies_and_forces(name):
+    from flashmd.simulation import LangevinSimulation
+    g = load_golden(name)
+    model, schnet, configs = dropin_model_from_golden(g)
+    for dtype, tag, tol in ((torch.float32, "ref32", 2e-5), (torch.float64, "ref64", 1e-10)):
+        data = LangevinSimulation.collate(deepcopy(configs))
+        data.pos = data.pos.to(dtype)
+        m = deepcopy(model).to(dtype)
+        data = m(data)
+        for k in ("SchNet", "bonds", "angles", "dihedrals", "repulsion"):
+            assert rel_l2(data.out[k]["energy"].detach(), g[f"{tag}.energy.{k}"]) < tol, (k, tag)
+            assert rel_l2(data.out[k]["forces"].detach(), g[f"{tag}.forces.{k}"]) < max(tol, 3e-5 if dtype == torch.float32 else 0), (k, tag)
+        assert rel_l2(data.out["energy"].detach(), g[f"{tag}.energy.total"]) < tol
+        assert rel_l2(data.out["forces"].detach(), g[f"{tag}.forces.total"]) < max(tol, 3e-5 if dtype == torch.float32 else 0)
+    # the neighbour list the model builds is the reference's, bit for bit
+    data = LangevinSimulation.collate(deepcopy(configs))
+    nl = schnet.neighbor_list(data, float(g["sys.cutoff"]), 1000)["SchNet"]["index_mapping"].numpy()
+    assert np.array_equal(nl, g["ref.schnet_edge_index"])
+
+
+def test_langevin_simulation_reproduces_reference_trajectory_files(tmp_path):
+    from flashmd.simulation import LangevinSimulation
+    g = load_golden("schnet_n54_b4.npz")
+    t = load_golden("langevin_n54_b4.npz")
+    dt, friction, beta, seed = (float(v) for v in t["params"])
+    model, _, configs = dropin_model_from_golden(g)
+    torch.manual_seed(1234)
+    sim = LangevinSimulation(friction=friction, dt=dt, n_timesteps=10, save_interval=1, export_interval=10,
+                             save_forces=True, save_energies=True, random_seed=int(seed), device="cpu", dtype="single",
+                             filename="g", output_dir=str(tmp_path), specialize_priors=True, compile_model=False,
+                             gptq=None, create_checkpoints=True)
+    sim.attach_model_and_configurations(model, configs, beta=beta)
+    assert np.allclose(sim.initial_data.velocities.numpy(), t["v0"], rtol=0, atol=0)
+    sim.simulate()
+    coords = np.load(tmp_path / "g_coords_0000.npy")
+    assert coords.shape == t["coords"].shape == (4, 10, 54, 3)
+    assert rel_l2(coords, t["coords"]) < 1e-5
+    assert rel_l2(np.load(tmp_path / "g_forces_0000.npy"), t["forces"]) < 1e-3     # chaotic growth over 10 steps
+    assert rel_l2(np.load(tmp_path / "g_potential_0000.npy"), t["potential"]) < 1e-4
+    assert rel_l2(np.load(tmp_path / "g_kineticenergy_0000.npy"), t["kinetic"]) < 1e-4
+    ours = sorted(f for f in os.listdir(tmp_path))
+    for f in ("g_coords_0000.npy", "g_forces_0000.npy", "g_potential_0000.npy", "g_kineticenergy_0000.npy",
+              "g_checkpoint_init.pt", "g_checkpoint_0000.pt", "g_specialized_model_and_config.pt"):
+        assert f in ours
+    m = sim.get_throughput_metrics()
+    assert m["path"] == "module" and m["throughput_timestep_mol_per_s"] > 0
+    # restart from the checkpoint continues instead of starting over
+    sim2 = LangevinSimulation(friction=friction, dt=dt, n_timesteps=20, save_interval=1, export_interval=10,
+                              random_seed=int(seed), device="cpu", filename="g", output_dir=str(tmp_path), gptq=None,
+                              read_checkpoint_file=True)
+    sim2.attach_model_and_configurations(model, configs, beta=beta)
+    assert sim2.current_timestep == 1
+    assert np.allclose(sim2.initial_data.pos.numpy().reshape(4, 54, 3), coords[:, -1], atol=1e-6)
+    sim2.simulate(overwrite=True)
+    assert os.path.exists(tmp_path / "g_coords_0001.npy")
+
+
+def test_pt_simulation_bookkeeping_matches_reference(tmp_path):
+    from flashmd.simulation import PTSimulation
+    from flashmd import synthetic
+    p = load_golden("pt_n24.npz")
+    betas = [float(b) for b in p["betas"]]
+    # same tiny system/model family as the golden (weights are irrelevant for the bookkeeping)
+    system = synthetic.synthetic_system(2, 24, seed=5, target_degree=12)
+    g = {"sys." + k: v for k, v in system.items() if k != "stats"}
+    st = system["stats"]
+    g |= {"stats.bonds.k": st["bonds"]["k"], "stats.bonds.x_0": st["bonds"]["x_0"], "stats.angles.k": st["angles"]["k"],
+          "stats.angles.x_0": st["angles"]["x_0"], "stats.dihedrals.k1_central": st["dihedrals"]["k1_central"],
+          "stats.dihedrals.k2_central": st["dihedrals"]["k2_central"], "stats.dihedrals.v0_central": st["dihedrals"]["v0_central"],
+          "stats.repulsion.sigma": st["repulsion"]["sigma"], "meta.hparams": np.array([32, 32, 16, 1, 16])}
+    from flashmd.engine import random_schnet_tensors
+    g |= {"w." + k: v.numpy() for k, v in random_schnet_tensors(5, 16, 32, 32, 1, (16,), synthetic.N_BEAD_TYPES + 1).items()}
+    model, _, configs = dropin_model_from_golden(g)
+    torch.manual_seed(99)
+    sim = PTSimulation(friction=1.0, dt=0.004, n_timesteps=40, save_interval=10, export_interval=40,
+                       exchange_interval=10, save_energies=True, random_seed=7, device="cpu", dtype="single",
+                       filename="pt", output_dir=str(tmp_path), specialize_priors=True, compile_model=False, gptq=None)
+    sim.attach_model_and_configurations(model, configs, betas=betas)
+    assert sim.n_indep_sims == int(p["n_indep"]) and np.allclose(sim.beta.numpy(), p["beta_per_sim"])
+    assert np.array_equal(sim._even_pairs[0].numpy(), p["even_a"]) and np.array_equal(sim._even_pairs[1].numpy(), p["even_b"])
+    assert np.array_equal(sim._odd_pairs[0].numpy(), p["odd_a"]) and np.array_equal(sim._odd_pairs[1].numpy(), p["odd_b"])
+    assert np.array_equal(sim.pair_to_beta_idx.numpy(), p["pair_to_beta_idx"])
+    # two exchange rounds on the recorded energies / coordinates with the reference's RNG draws
+    data = deepcopy(sim.initial_data)
+    for rnd in range(2):
+        data.pos = torch.from_numpy(p[f"round{rnd}.x_before"].copy())
+        data.velocities = torch.from_numpy(p[f"round{rnd}.v_before"].copy())
+        data.out = {"energy": torch.from_numpy(p[f"round{rnd}.energies"].copy())}
+        torch.manual_seed(1000 + rnd)
+        data = sim.detect_and_exchange_replicas(data)
+        assert np.array_equal(data.pos.numpy(), p[f"round{rnd}.x_after"])
+        assert np.allclose(data.velocities.numpy(), p[f"round{rnd}.v_after"], rtol=1e-6, atol=0)
+        assert np.array_equal(sim.acceptance_matrix.numpy(), p[f"round{rnd}.acceptance_matrix"])
+    sim._propose_even_pairs = True
+    sim.acceptance_matrix.zero_()
+    sim.simulate(overwrite=True)
+    assert sorted(os.listdir(tmp_path)) == sorted(str(f) for f in p["files"])
+    assert tuple(np.load(tmp_path / "pt_coords_0000.npy").shape) == tuple(p["coords_shape"])
+
+
+def test_toggles_and_known_answers():
+    from flashmd.models import CosineCutoff, GaussianBasis, IdentityCutoff, ShiftedCosineCutoff, StandardSchNet
+    from flashmd.models import schnet as S
+    k = load_golden("known_answers.npz")
+    d = torch.from_numpy(k["d"])
+    assert np.allclose(CosineCutoff(0, 5)(d).numpy(), k["cos_0_5"], atol=1e-7)
+    assert np.allclose(CosineCutoff(0, 10)(d).numpy(), k["cos_0_10"], atol=1e-7)
+    assert np.allclose(CosineCutoff(5, 10)(d).numpy(), k["cos_5_10"], atol=1e-7)
+    assert np.allclose(ShiftedCosineCutoff(5, 0.5)(d).numpy(), k["shifted_5_05"], atol=1e-7)
+    gb = GaussianBasis(CosineCutoff(0.0, 10.0), num_rbf=50)
+    assert np.allclose(gb.offset.numpy(), k["gauss_centers"]) and np.isclose(float(gb.coeff), float(k["gauss_gamma"]))
+    assert np.allclose(gb(d).numpy(), k["gauss_val"], atol=1e-7)
+    assert isinstance(GaussianBasis(10).cutoff, IdentityCutoff)          # reference tests/models/radial_basis
+    with pytest.raises(ValueError):
+        CosineCutoff(10, 5)
+    with pytest.raises(ValueError):
+        StandardSchNet(gb, CosineCutoff(0, 10), [8], num_interactions=0)
+    with pytest.warns(UserWarning):
+        StandardSchNet(gb, CosineCutoff(0, 5), [8], hidden_channels=8, num_filters=8, embedding_size=4)
+    for name in ("USE_TRITON_MESSAGE_PASSING", "USE_FUSED_RBF", "USE_FUSED_TANH_LINEAR", "USE_CSR", "USE_SRC_CSR_GRAD_X"):
+        assert hasattr(S, name)
+
+
+def test_cli_config1_cpu_disable_optim(tmp_path):
+    """BASELINE config[0]: random-init CGSchNet, synthetic 1ENH-sized CG system (54 beads), batch 4, Langevin
+    steps on CPU with --disable_optim, driven through the `flashmd-langevin` entry point + YAML config."""
+    import subprocess
+    import sys
+    import yaml
+    from helpers import ROOT_DIR
+    g = load_golden("schnet_n54_b4.npz")
+    model, _, configs = dropin_model_from_golden(g)
+    torch.save(model, tmp_path / "model.pt")
+    torch.save(configs[:2], tmp_path / "structures.pt")
+    cfg = yaml.safe_load(open(os.path.join(ROOT_DIR, "examples", "langevin.yaml")))
+    cfg["simulation"].update(n_timesteps=20, save_interval=5, export_interval=10, log_interval=10, device="cpu",
+                             filename="run", output_dir=str(tmp_path), save_energies=True)
+    cfg.update(model_file=str(tmp_path / "model.pt"), structure_file=str(tmp_path / "structures.pt"))
+    yaml.safe_dump(cfg, open(tmp_path / "cfg.yaml", "w"))
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT_DIR, "flash-molecular-dynamics_b200"))
+    r = subprocess.run([sys.executable, "-m", "flashmd.scripts.nvt_langevin", "--config", str(tmp_path / "cfg.yaml"),
+                        "--batch_size", "4", "--simulation.friction", "2.0", "--disable_optim"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    c0, c1 = np.load(tmp_path / "run_coords_0000.npy"), np.load(tmp_path / "run_coords_0001.npy")
+    assert c0.shape == c1.shape == (4, 2, 54, 3) and np.isfinite(c1).all()
+    assert os.path.exists(tmp_path / "run_config.yaml") and os.path.exists(tmp_path / "run_log.txt")
+    assert '"path": "module"' in r.stdout

@@ -1,0 +1,124 @@
+"""GPU tests of the reference-facing objects: model modules through the operator-level kernels
+(`flashmd.kernels`, autograd), and LangevinSimulation / PTSimulation through the fused engine."""
+import os
+from copy import deepcopy
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import dropin_model_from_golden, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz"])
+def test_module_path_on_gpu_uses_kernels_and_matches_reference(name):
+    """SumOut(GradientsOut(StandardSchNet), priors) on CUDA: fused RBF, CSR CFConv (+ exact cut-off gradient),
+    fused tanh-linear operators with autograd; fp32 energies/forces within 1e-5 of the reference."""
+    from flashmd.simulation import LangevinSimulation
+    g = load_golden(name)
+    model, schnet, configs = dropin_model_from_golden(g)
+    data = LangevinSimulation.collate(deepcopy(configs)).to(DEV)
+    model = model.to(DEV).eval()
+    for p_ in model.parameters():          # weights are frozen in simulations (reference base.py:357-358);
+        p_.requires_grad_(False)           # the operators provide d/d(pos) only
+    torch.backends.cuda.matmul.allow_tf32 = False
+    data = model(data)
+    assert rel_l2(data.out["SchNet"]["energy"].cpu(), g["ref64.energy.SchNet"]) < 1e-5
+    assert rel_l2(data.out["SchNet"]["forces"].cpu(), g["ref64.forces.SchNet"]) < 1e-5
+    assert rel_l2(data.out["forces"].cpu(), g["ref64.forces.total"]) < 3e-5
+    assert rel_l2(data.out["energy"].cpu(), g["ref64.energy.total"]) < 1e-5
+
+
+def test_gptq_modules_on_gpu():
+    from oracle import fmd_oracle as O
+    from helpers import golden_params, golden_system
+    from flashmd.models import GradientsOut, apply_gptq_w16a16_to_model, validate_gptq_w16a16
+    from flashmd.simulation import LangevinSimulation
+    g = load_golden("schnet_n54_b4.npz")
+    model, schnet, configs = dropin_model_from_golden(g)
+    net = GradientsOut(apply_gptq_w16a16_to_model(schnet)).to(DEV).eval()
+    for p_ in net.parameters():
+        p_.requires_grad_(False)
+    assert validate_gptq_w16a16(net)
+    data = LangevinSimulation.collate(deepcopy(configs)).to(DEV)
+    data = net(data)
+    pos, types, batch, ptr, B, n = golden_system(g)
+    e_ref, f_ref = O.schnet_energy_forces(golden_params(g), pos, types, batch, B,
+                                          torch.from_numpy(g["ref.schnet_edge_index"]), precision="w16a16")
+    assert rel_l2(data.out["SchNet"]["forces"].cpu(), f_ref) < 1e-2
+    assert rel_l2(data.out["SchNet"]["energy"].cpu(), e_ref) < 1e-2
+
+
+@pytest.mark.parametrize("gptq", [None, "w16a16"])
+def test_langevin_simulation_fused_engine(tmp_path, gptq):
+    """Same object protocol as on CPU; the step runs as one CUDA-graph replay of the fused engine."""
+    from flashmd.simulation import LangevinSimulation
+    g = load_golden("schnet_n54_b4.npz")
+    t = load_golden("langevin_n54_b4.npz")
+    model, _, configs = dropin_model_from_golden(g)
+    torch.manual_seed(1234)
+    sim = LangevinSimulation(friction=1.0, dt=0.004, n_timesteps=10, save_interval=1, export_interval=10,
+                             save_forces=True, save_energies=True, random_seed=103838, device=DEV, dtype="single",
+                             filename="g", output_dir=str(tmp_path), specialize_priors=True, gptq=gptq,
+                             noise_source="torch", create_checkpoints=True)
+    sim.attach_model_and_configurations(model, configs, beta=1.67)
+    sim.initial_data.velocities = torch.from_numpy(t["v0"]).to(DEV)
+    noise = torch.from_numpy(t["noise"]).to(DEV)
+    step = {"i": 0}
+
+    def inject(eng):          # the reference drew its noise from a CPU generator: replay exactly those numbers
+        eng.noise_buf.copy_(noise[step["i"]])
+        step["i"] += 1
+        eng.step()
+    sim._engine_timestep = inject
+    sim.simulate()
+    assert sim.get_throughput_metrics()["path"] == "fused-engine"
+    coords = np.load(tmp_path / "g_coords_0000.npy")
+    tol = 1e-5 if gptq is None else 1e-4
+    assert coords.shape == (4, 10, 54, 3) and rel_l2(coords, t["coords"]) < tol
+    assert rel_l2(np.load(tmp_path / "g_potential_0000.npy"), t["potential"]) < (1e-4 if gptq is None else 1e-2)
+    assert rel_l2(np.load(tmp_path / "g_kineticenergy_0000.npy"), t["kinetic"]) < (1e-4 if gptq is None else 1e-3)
+    assert rel_l2(np.load(tmp_path / "g_forces_0000.npy"), t["forces"]) < (1e-3 if gptq is None else 2e-2)
+    assert os.path.exists(tmp_path / "g_checkpoint_0000.pt")
+
+
+def test_langevin_simulation_philox_temperature(tmp_path):
+    """Default noise (in-kernel Philox): equipartition <KE> = 3 N / (2 beta) after equilibration."""
+    from flashmd.simulation import LangevinSimulation
+    g = load_golden("schnet_n54_b4.npz")
+    model, _, configs = dropin_model_from_golden(g)
+    cfgs = [deepcopy(configs[i % 4]) for i in range(32)]
+    sim = LangevinSimulation(friction=1.0, dt=0.004, n_timesteps=3000, save_interval=10, save_energies=True,
+                             random_seed=5, device=DEV, gptq="w16a16")
+    sim.attach_model_and_configurations(model, cfgs, beta=1.67)
+    sim.simulate()
+    ke = sim.simulated_kinetic_energies[:, 100:]            # [n_sims, frames]
+    expect = 1.5 * 54 / 1.67
+    assert abs(float(ke.mean()) / expect - 1.0) < 0.03, (float(ke.mean()), expect)
+    assert np.isfinite(sim.simulated_coords).all()
+
+
+def test_pt_simulation_fused_engine(tmp_path):
+    from flashmd.simulation import PTSimulation
+    g = load_golden("schnet_n54_b4.npz")
+    model, _, configs = dropin_model_from_golden(g)
+    betas = [1.67, 1.42, 1.16]
+    sim = PTSimulation(friction=1.0, dt=0.004, n_timesteps=200, save_interval=10, export_interval=100,
+                       exchange_interval=20, save_energies=True, random_seed=7, device=DEV, filename="pt",
+                       output_dir=str(tmp_path), gptq="w16a16", exchange_rng="philox")
+    sim.attach_model_and_configurations(model, configs, betas=betas)
+    sim.simulate()
+    assert sim.get_throughput_metrics()["path"] == "fused-engine"
+    assert sim.exchange_summary["attempted"] == 10 * 4 and 0 <= sim.exchange_summary["ratio"] <= 1
+    # like the reference, the acceptance file is written BEFORE the exchange of the same step and is numbered
+    # one higher than the coordinate file of that export: 4 rounds, then 5 rounds, x 4 pairs
+    acc = np.load(tmp_path / "pt_acceptance_0001.npy")
+    assert acc.shape == (3, 3) and acc.sum() == 4 * 4
+    assert np.load(tmp_path / "pt_acceptance_0002.npy").sum() == 5 * 4
+    assert np.load(tmp_path / "pt_coords_0001.npy").shape == (12, 10, 54, 3)
+    # hotter replicas carry more kinetic energy
+    ke = np.load(tmp_path / "pt_kineticenergy_0001.npy").reshape(3, 4, -1).mean(axis=(1, 2))
+    assert ke[0] < ke[2]
