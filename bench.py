@@ -238,6 +238,7 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("FMD_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

@@ -57,6 +57,16 @@ class PTSimulation(LangevinSimulation):
         self.n_indep_sims, self.n_replicas = len(configurations), len(betas)
         extended = [deepcopy(c) for _ in betas for c in configurations]
         ext_betas = [b for b in betas for _ in configurations]
+        # multi-GPU: the replicas are sharded contiguously over the ranks (simulation/distributed.py)
+        from .distributed import ShardedExchange, dist_info, shard_range
+        rank, world = dist_info()
+        self._sharded = None
+        if world > 1:
+            lo, hi = shard_range(len(extended), rank, world)
+            self._sharded = ShardedExchange(torch.tensor(ext_betas), len(configurations[0].atom_types), rank, world)
+            extended, ext_betas = extended[lo:hi], ext_betas[lo:hi]
+            if self.filename is not None and not self.filename.endswith(f"_rank{rank}"):
+                self.filename = f"{self.filename}_rank{rank}"
         super()._attach_configurations(extended, ext_betas)
         self._propose_even_pairs = True
         self._even_pairs, self._odd_pairs = adjacent_pairs(self.n_replicas, self.n_indep_sims)
@@ -114,6 +124,13 @@ class PTSimulation(LangevinSimulation):
     def _engine_subroutine(self, eng):
         from .. import _lib as L
         pair_a, pair_b = self._get_proposed_pairs()
+        if self._sharded is not None:
+            from .distributed import exchange_uniforms
+            uni = exchange_uniforms(self.random_seed or 0, self._exchange_index, len(pair_a))
+            acc = self._sharded.exchange(eng.pos, eng.vel, eng.ff.energy, pair_a, pair_b, uni)
+            self._exchange_index += 1
+            self._record(pair_a, pair_b, acc)
+            return
         dev = eng.pos.device
         pa = pair_a.to(dev, torch.int32).contiguous()
         pb = pair_b.to(dev, torch.int32).contiguous()
