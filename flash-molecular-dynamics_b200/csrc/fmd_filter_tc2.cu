@@ -24,8 +24,9 @@ constexpr uint32_t O_WF0 = 0;                                // 16 KB
 constexpr uint32_t O_WF1 = O_WF0 + 128 * 128;                // 32 KB
 constexpr uint32_t O_RBF = O_WF1 + 2 * 128 * 128;            // 2 x 16 KB
 constexpr uint32_t O_TT = O_RBF + 2 * 128 * 128;             // 2 x 32 KB
-constexpr uint32_t O_META = O_TT + 2 * 2 * 128 * 128;        // 4 x 1 KB: {x offset, C(d)} per edge
-constexpr uint32_t O_OWN = O_META + META_STAGES * TILE * 8;  // 4 x 512 B: segment owner per edge
+constexpr uint32_t O_XOFF = O_TT + 2 * 2 * 128 * 128;        // 4 x 512 B: element offset nbr*NF of the gathered row
+constexpr uint32_t O_CUT = O_XOFF + META_STAGES * TILE * 4;  // 4 x 512 B: C(d_e)
+constexpr uint32_t O_OWN = O_CUT + META_STAGES * TILE * 4;   // 4 x 512 B: segment owner per edge
 constexpr uint32_t O_HEAD = O_OWN + META_STAGES * TILE * 4;  // 4 x 32 B: {prev_owner, -, -, -, boundary mask[4]}
 constexpr uint32_t O_BIAS = O_HEAD + META_STAGES * 32;
 constexpr uint32_t O_CEN = O_BIAS + NF * 4;
@@ -35,7 +36,7 @@ constexpr uint32_t SMEM2_ALLOC = SMEM2 + 1024;
 
 // barrier indices
 enum { B_RBF_FULL = 0, B_RBF_EMPTY = 2, B_D1_FULL = 4, B_D1_EMPTY = 6, B_TT_FULL = 8, B_TT_EMPTY = 10,
-       B_D2_FULL = 12, B_D2_EMPTY = 14, B_META_EMPTY = 16, B_COUNT = 20 };
+       B_D2_FULL = 12, B_D2_EMPTY = 14, B_META_EMPTY = 16, B_META_FULL = 20, B_COUNT = 24 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restrict__ edge_owner,
@@ -74,7 +75,10 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_init(bar(B_D2_FULL + i), 1);
       mbar_init(bar(B_D2_EMPTY + i), 128);
     }
-    for (int i = 0; i < META_STAGES; ++i) mbar_init(bar(B_META_EMPTY + i), 128);
+    for (int i = 0; i < META_STAGES; ++i) {
+      mbar_init(bar(B_META_EMPTY + i), 256);   // consumed by the tanh warps (cut) and one epilogue group
+      mbar_init(bar(B_META_FULL + i), 128);
+    }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -117,11 +121,12 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       const uint32_t bmask = __ballot_sync(0xffffffffu, valid && tid > 0 && own != prev);
       mbar_wait_guard(bar(B_META_EMPTY + ms), mph ^ 1);
       mbar_wait_guard(bar(B_RBF_EMPTY + s), ph ^ 1);
-      reinterpret_cast<uint2*>(smem + O_META + ms * TILE * 8)[tid] =
-          make_uint2((uint32_t)nb * (uint32_t)NF, __float_as_uint(cut));
+      reinterpret_cast<uint32_t*>(smem + O_XOFF + ms * TILE * 4)[tid] = (uint32_t)nb * (uint32_t)NF;
+      reinterpret_cast<float*>(smem + O_CUT + ms * TILE * 4)[tid] = cut;
       reinterpret_cast<int*>(smem + O_OWN + ms * TILE * 4)[tid] = own;
       if (tid == 0) *reinterpret_cast<int*>(smem + O_HEAD + ms * 32) = prev;
       if (lane == 0) reinterpret_cast<uint32_t*>(smem + O_HEAD + ms * 32 + 16)[warp] = bmask;
+      mbar_arrive(bar(B_META_FULL + ms));
       write_rbf_row_fast(smem + O_RBF + s * (128 * 128), sCen, tid, d, cut, g2);
       fence_async_smem();
       mbar_arrive(bar(B_RBF_FULL + s));
@@ -171,12 +176,13 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     const float bias = sBias[j];
     for (int i = 0; i < n_my; ++i) {
-      const int s = i & 1;
+      const int s = i & 1, ms = i & (META_STAGES - 1);
       const uint32_t ph = (i >> 1) & 1;
       mbar_wait_guard(bar(B_D1_FULL + s), ph);
       mbar_wait_guard(bar(B_TT_EMPTY + s), ph ^ 1);
       fence_after_sync();
       uint8_t* sTT = smem + O_TT + s * (2 * 128 * 128);
+      const float4* sCut4 = reinterpret_cast<const float4*>(smem + O_CUT + ms * TILE * 4);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
@@ -184,11 +190,14 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          // t * C(d_e): D2 is linear in t, so the cut-off rides through the second GEMM for free
+          const float4 ca = sCut4[c * 8 + q * 2], cb = sCut4[c * 8 + q * 2 + 1];
+          const float cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
           uint32_t p[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            p[u] = pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u]) + bias),
-                              tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]) + bias));
+            p[u] = pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u]) + bias) * cc[2 * u],
+                              tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]) + bias) * cc[2 * u + 1]);
           const int chunk = c * 4 + q;
           *reinterpret_cast<uint4*>(sTT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7)) =
               make_uint4(p[0], p[1], p[2], p[3]);
@@ -196,6 +205,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       }
       fence_before_sync();
       mbar_arrive(bar(B_D1_EMPTY + s));
+      mbar_arrive(bar(B_META_EMPTY + ms));
       fence_async_smem();
       mbar_arrive(bar(B_TT_FULL + s));
     }
@@ -207,13 +217,25 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
     const float* __restrict__ xf = x + f;
     for (int i = g; i < n_my; i += 2) {
       const int ms = i & (META_STAGES - 1);
-      const uint32_t ph = (i >> 1) & 1;
+      const uint32_t ph = (i >> 1) & 1, mph = (i / META_STAGES) & 1;
       const int tile = blockIdx.x + i * gridDim.x;
-      const uint4* sMeta2 = reinterpret_cast<const uint4*>(smem + O_META + ms * TILE * 8);  // two edges per uint4
+      const uint4* sOff4 = reinterpret_cast<const uint4*>(smem + O_XOFF + ms * TILE * 4);
       const int* sOwn = reinterpret_cast<const int*>(smem + O_OWN + ms * TILE * 4);
       const uint32_t* sMask = reinterpret_cast<const uint32_t*>(smem + O_HEAD + ms * 32 + 16);
-      mbar_wait_guard(bar(B_D2_FULL + g), ph);
-      fence_after_sync();
+      // gather of x rows for 16 edges: independent of the GEMMs, so the first chunk is in flight before D2 is ready
+      auto gather16 = [&](float (&xv)[16], int c16) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint4 o = sOff4[c16 * 4 + u];
+          xv[4 * u] = __ldg(xf + o.x);
+          xv[4 * u + 1] = __ldg(xf + o.y);
+          xv[4 * u + 2] = __ldg(xf + o.z);
+          xv[4 * u + 3] = __ldg(xf + o.w);
+        }
+      };
+      mbar_wait_guard(bar(B_META_FULL + ms), mph);
+      float xa[16], xb[16];
+      gather16(xa, 0);
       int cur = sOwn[0];
       bool head = *reinterpret_cast<const int*>(smem + O_HEAD + ms * 32) == cur;  // run began in an earlier tile
       float acc = 0.f;
@@ -224,32 +246,36 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         cur = next_owner;
         acc = 0.f;
       };
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem + 256 + g * 128 + lane_sel + c * 32, r);
-        float xv[32];
+      auto consume16 = [&](const uint32_t (&r)[16], const float (&xv)[16], int c16) {
+        const uint32_t bits = (sMask[c16 >> 1] >> ((c16 & 1) * 16)) & 0xffffu;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const uint4 m = sMeta2[c * 16 + u];
-          xv[2 * u] = __ldg(xf + m.x) * __uint_as_float(m.y);
-          xv[2 * u + 1] = __ldg(xf + m.z) * __uint_as_float(m.w);
-        }
-        const uint32_t bits = sMask[c];
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           if (((bits >> (8 * q)) & 0xffu) == 0u) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) acc = fmaf(__uint_as_float(r[q * 8 + u]), xv[q * 8 + u], acc);
           } else {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              if ((bits >> (8 * q + u)) & 1u) flush(sOwn[c * 32 + q * 8 + u]);
+              if ((bits >> (8 * q + u)) & 1u) flush(sOwn[c16 * 16 + q * 8 + u]);
               acc = fmaf(__uint_as_float(r[q * 8 + u]), xv[q * 8 + u], acc);
             }
           }
         }
+      };
+      mbar_wait_guard(bar(B_D2_FULL + g), ph);
+      fence_after_sync();
+      const uint32_t d2 = tmem + 256 + g * 128 + lane_sel;
+#pragma unroll 1
+      for (int c16 = 0; c16 < 8; c16 += 2) {
+        uint32_t r[16];
+        tmem_ld16(d2 + c16 * 16, r);
+        gather16(xb, c16 + 1);
+        tmem_ld_wait();
+        consume16(r, xa, c16);
+        tmem_ld16(d2 + (c16 + 1) * 16, r);
+        if (c16 + 2 < 8) gather16(xa, c16 + 2);
+        tmem_ld_wait();
+        consume16(r, xb, c16 + 1);
       }
       fence_before_sync();
       mbar_arrive(bar(B_D2_EMPTY + g));
