@@ -18,6 +18,14 @@ using namespace fmd::filt;
 namespace {
 
 constexpr int NTHREADS = 17 * 32;
+
+// Optional timeline trace (tools only; scripts/trace_roles.py): when set, CTA 0 records clock64() stamps
+// {wait start, work start, end} per role and tile into trace[role][tile < 64][3].
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_stamp(int role, int tile, int k, bool leader) {
+  if (g_trace != nullptr && blockIdx.x == 0 && leader && tile < 64)
+    g_trace[(role * 64 + tile) * 3 + k] = (unsigned long long)clock64();
+}
 constexpr int META_STAGES = 4;
 
 constexpr uint32_t O_WF0 = 0;                                // 16 KB
@@ -291,20 +299,20 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
 // =================================================================================================
 // Backward (see fmd_filter_tc.cu for the math), warp-specialised:
 //   PE warps 0-3   thread-per-edge: produce(i) = metadata + rbf row; e4(i-2) = D4 -> g_d
-//   G0 warps 4-7   thread-per-feature: row f of gW0^T = a[nbr,f] * g_m[owner,f] for even tiles
+//   G0 warps 4-7   thread-per-feature, even tiles: row f of gW0^T = a[nbr,f] * g_m[owner,f]; then D1 -> t (stash)
 //   G1 warps 8-11  same for odd tiles
-//   T  warps 12-15 thread-per-feature: A(i) = D1 -> t (stashed in smem); B(i) = D3 -> g_t row + cut-term sums
+//   T  warps 12-15 thread-per-feature: D3 -> g_t row (in place over t) + cut-term sums
 //   M  warp  16    MMA issue: D13[s] = Wf0.rbf^T ; D13[s] = Wf1^T.gW0^T ; D4[s] = g_t.Wf0
 constexpr uint32_t BO_WF0 = 0;
 constexpr uint32_t BO_WF1 = BO_WF0 + 128 * 128;
 constexpr uint32_t BO_RBF = BO_WF1 + 2 * 128 * 128;          // 2 x 16 KB
-constexpr uint32_t BO_OP = BO_RBF + 2 * 128 * 128;           // 2 x 32 KB: gW0^T, then g_t^T
-constexpr uint32_t BO_ST = BO_OP + 2 * 2 * 128 * 128;        // 2 x 32 KB: t^T stash
+constexpr uint32_t BO_OP = BO_RBF + 2 * 128 * 128;           // 2 x 32 KB: gW0^T (B operand of MMA3)
+constexpr uint32_t BO_ST = BO_OP + 2 * 2 * 128 * 128;        // 2 x 32 KB: t^T stash, overwritten in place by g_t^T (A operand of MMA4)
 constexpr uint32_t BO_META = BO_ST + 2 * 2 * 128 * 128;      // 4 x 1 KB
 constexpr uint32_t BO_OWN = BO_META + META_STAGES * TILE * 8;
 constexpr uint32_t BO_HEAD = BO_OWN + META_STAGES * TILE * 4;  // 4 x 16 B boundary masks
-constexpr uint32_t BO_RED = BO_HEAD + META_STAGES * 16;      // 2 x [4][128] floats
-constexpr uint32_t BO_BIAS = BO_RED + 2 * 4 * TILE * 4;
+constexpr uint32_t BO_RED = BO_HEAD + META_STAGES * 16;      // 4 x [4][128] floats
+constexpr uint32_t BO_BIAS = BO_RED + 4 * 4 * TILE * 4;
 constexpr uint32_t BO_CEN = BO_BIAS + NF * 4;
 constexpr uint32_t BO_BAR = BO_CEN + RP * 4;
 constexpr uint32_t BSMEM = BO_BAR + 40 * 8 + 16;
@@ -312,8 +320,9 @@ constexpr uint32_t BSMEM_ALLOC = BSMEM + 1024;
 static_assert(BSMEM_ALLOC <= 232448, "backward kernel exceeds the 227 KB shared-memory limit");
 
 enum { C_RBF_FULL = 0, C_RBF_EMPTY = 2, C_D1_FULL = 4, C_D1_EMPTY = 6, C_GW_FULL = 8, C_D3_FULL = 10, C_D3_EMPTY = 12,
-       C_GT_FULL = 14, C_OP_EMPTY = 16, C_D4_FULL = 18, C_D4_EMPTY = 20, C_META_FULL = 22, C_META_EMPTY = 26,
-       C_COUNT = 30 };
+       C_GT_FULL = 14, C_OP_EMPTY = 16, C_D4_FULL = 18, C_D4_EMPTY = 22, C_META_FULL = 26, C_META_EMPTY = 30,
+       C_ST_EMPTY = 34, C_ST_FULL = 36, C_COUNT = 38 };
+constexpr int D4_STAGES = 4;   // D4 (64 columns) is quadruple-buffered so that e4 may lag 4 tiles behind produce
 
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
 
@@ -355,6 +364,10 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_init(bar(C_D3_EMPTY + i), 128);
       mbar_init(bar(C_GT_FULL + i), 128);
       mbar_init(bar(C_OP_EMPTY + i), 1);
+      mbar_init(bar(C_ST_EMPTY + i), 1);
+      mbar_init(bar(C_ST_FULL + i), 128);
+    }
+    for (int i = 0; i < D4_STAGES; ++i) {
       mbar_init(bar(C_D4_FULL + i), 1);
       mbar_init(bar(C_D4_EMPTY + i), 128);
     }
@@ -373,7 +386,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: D13[s] at s*128, D4[s] at 256 + s*64
+  // TMEM columns: D13[s] at s*128 (s = tile & 1), D4[q] at 256 + q*64 (q = tile & 3)
 
   if (warp < 4) {
     // =========================================================== PE: produce(i), then e4(i-2)
@@ -393,12 +406,16 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         if (e > 0) prev_n = __ldg(&edge_owner[e - 1]);
       }
     };
-    float dq[3] = {0.f, 0.f, 0.f}, cq[3] = {0.f, 0.f, 0.f};  // (dist, cut) of tiles i, i-1, i-2
+    float dq[D4_STAGES] = {0.f, 0.f, 0.f, 0.f}, cq[D4_STAGES] = {0.f, 0.f, 0.f, 0.f};  // (dist, cut) of tiles i-1 .. i-4
     auto e4 = [&](int i, float d, float cut) {
-      const int s = i & 1;
-      const uint32_t ph = (i >> 1) & 1;
+      const int s = i & (D4_STAGES - 1);
+      const uint32_t ph = (i / D4_STAGES) & 1;
       const int e = (blockIdx.x + i * gridDim.x) * TILE + tid;
+      float prev_gd = 0.f;
+      if (accumulate && e < E) prev_gd = g_d[e];
+      trace_stamp(1, i, 0, tid == 0);
       mbar_wait_guard(bar(C_D4_FULL + s), ph);
+      trace_stamp(1, i, 1, tid == 0);
       fence_after_sync();
       const float dcut = d < rc ? -0.5f * pi_over_rc * __sinf(d * pi_over_rc) : 0.f;
       const float two_g = 2.0f * gamma;
@@ -422,7 +439,8 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       }
       fence_before_sync();
       mbar_arrive(bar(C_D4_EMPTY + s));
-      if (e < E) g_d[e] = accumulate ? g_d[e] + acc : acc;
+      if (e < E) g_d[e] = prev_gd + acc;
+      trace_stamp(1, i, 2, tid == 0);
     };
     if (n_my > 0) prefetch(tile);
     for (int i = 0; i < n_my; ++i, tile += gridDim.x) {
@@ -434,8 +452,10 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       const bool valid = own >= 0;
       const float cut = valid ? cosine_cutoff_fast(d, pi_over_rc, rc) : 0.f;
       const uint32_t bmask = __ballot_sync(0xffffffffu, valid && tid > 0 && own != prev);
+      trace_stamp(0, i, 0, tid == 0);
       mbar_wait_guard(bar(C_META_EMPTY + ms), mph ^ 1);
       mbar_wait_guard(bar(C_RBF_EMPTY + s), ph ^ 1);
+      trace_stamp(0, i, 1, tid == 0);
       reinterpret_cast<uint2*>(smem + BO_META + ms * TILE * 8)[tid] =
           make_uint2((uint32_t)nb * (uint32_t)NF, __float_as_uint(cut));
       reinterpret_cast<int*>(smem + BO_OWN + ms * TILE * 4)[tid] = valid ? own : 0;
@@ -444,71 +464,38 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       fence_async_smem();
       mbar_arrive(bar(C_RBF_FULL + s));
       mbar_arrive(bar(C_META_FULL + ms));
-      dq[2] = dq[1]; dq[1] = dq[0]; dq[0] = d;
-      cq[2] = cq[1]; cq[1] = cq[0]; cq[0] = cut;
-      if (i >= 2) e4(i - 2, dq[2], cq[2]);
+      trace_stamp(0, i, 2, tid == 0);
+      if (i >= D4_STAGES) e4(i - D4_STAGES, dq[D4_STAGES - 1], cq[D4_STAGES - 1]);
+#pragma unroll
+      for (int k = D4_STAGES - 1; k > 0; --k) {
+        dq[k] = dq[k - 1];
+        cq[k] = cq[k - 1];
+      }
+      dq[0] = d;
+      cq[0] = cut;
     }
-    if (n_my >= 2) e4(n_my - 2, dq[1], cq[1]);
-    if (n_my >= 1) e4(n_my - 1, dq[0], cq[0]);
+    // drain: tiles n_my-4 .. n_my-1 sit in dq[3] .. dq[0]
+#pragma unroll
+    for (int k = D4_STAGES - 1; k >= 0; --k)
+      if (n_my - 1 - k >= 0) e4(n_my - 1 - k, dq[k], cq[k]);
   } else if (warp < 12) {
     // =========================================================== G0 / G1: gW0^T rows (thread = feature f)
     const int g = warp < 8 ? 0 : 1;
     const int f = (warp & 3) * 32 + lane;
     const float* __restrict__ af = a + f;
     const float* __restrict__ gmf = g_m + f;
-    for (int i = g; i < n_my; i += 2) {
-      const int ms = i & (META_STAGES - 1);
-      const uint32_t ph = (i >> 1) & 1, mph = (i / META_STAGES) & 1;
-      const uint4* sMeta2 = reinterpret_cast<const uint4*>(smem + BO_META + ms * TILE * 8);
-      const int* sOwn = reinterpret_cast<const int*>(smem + BO_OWN + ms * TILE * 4);
-      const uint32_t* sMask = reinterpret_cast<const uint32_t*>(smem + BO_HEAD + ms * 16);
-      uint8_t* sOp = smem + BO_OP + g * (2 * 128 * 128);
-      mbar_wait_guard(bar(C_META_FULL + ms), mph);
-      float gm = __ldg(gmf + (size_t)sOwn[0] * NF);
-      mbar_wait_guard(bar(C_OP_EMPTY + g), ph ^ 1);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float av[32];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const uint4 m = sMeta2[c * 16 + u];
-          av[2 * u] = __ldg(af + m.x);
-          av[2 * u + 1] = __ldg(af + m.z);
-        }
-        const uint32_t bits = sMask[c];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (((bits >> (8 * q)) & 0xffu) == 0u) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) av[q * 8 + u] *= gm;
-          } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if ((bits >> (8 * q + u)) & 1u) gm = __ldg(gmf + (size_t)sOwn[c * 32 + q * 8 + u] * NF);
-              av[q * 8 + u] *= gm;
-            }
-          }
-          const int chunk = c * 4 + q;
-          *reinterpret_cast<uint4*>(sOp + (chunk >> 3) * (128 * 128) + sw128_off(f, chunk & 7)) =
-              make_uint4(pack_half2(av[q * 8], av[q * 8 + 1]), pack_half2(av[q * 8 + 2], av[q * 8 + 3]),
-                         pack_half2(av[q * 8 + 4], av[q * 8 + 5]), pack_half2(av[q * 8 + 6], av[q * 8 + 7]));
-        }
-      }
-      fence_async_smem();
-      mbar_arrive(bar(C_GW_FULL + g));
-      mbar_arrive(bar(C_META_EMPTY + ms));
-    }
-  } else if (warp < 16) {
-    // =========================================================== T (thread = feature j)
-    const int j = (warp & 3) * 32 + lane;
-    const int wq = warp & 3;
-    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
-    const float bias = sBias[j];
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    const float bias = sBias[f];
+    // tanh phase of the same tile (D1 -> t -> stash), done by the gather group: these warps idle ~60 % of a tile
+    // period waiting for buffers, while the dedicated T warps are the longest role (timeline trace)
     auto phaseA = [&](int i) {
       const int s = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       uint8_t* sT = smem + BO_ST + s * (2 * 128 * 128);
+      trace_stamp(4, i, 0, f == 0);
       mbar_wait_guard(bar(C_D1_FULL + s), ph);
+      mbar_wait_guard(bar(C_ST_EMPTY + s), ph ^ 1);   // MMA4(i-2) has consumed g_t from sT[s]
+      trace_stamp(4, i, 1, f == 0);
       fence_after_sync();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -523,22 +510,92 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
             p[u] = pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u]) + bias),
                               tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]) + bias));
           const int chunk = c * 4 + q;
-          *reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7)) =
+          *reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(f, chunk & 7)) =
               make_uint4(p[0], p[1], p[2], p[3]);
         }
       }
       fence_before_sync();
       mbar_arrive(bar(C_D1_EMPTY + s));
+      mbar_arrive(bar(C_ST_FULL + s));
+      trace_stamp(4, i, 2, f == 0);
     };
+    for (int i = g; i < n_my; i += 2) {
+      const int ms = i & (META_STAGES - 1);
+      const uint32_t ph = (i >> 1) & 1, mph = (i / META_STAGES) & 1;
+      const uint4* sMeta2 = reinterpret_cast<const uint4*>(smem + BO_META + ms * TILE * 8);
+      const int* sOwn = reinterpret_cast<const int*>(smem + BO_OWN + ms * TILE * 4);
+      const uint32_t* sMask = reinterpret_cast<const uint32_t*>(smem + BO_HEAD + ms * 16);
+      uint8_t* sOp = smem + BO_OP + g * (2 * 128 * 128);
+      trace_stamp(2 + g, i, 0, f == 0);
+      mbar_wait_guard(bar(C_META_FULL + ms), mph);
+      float gm = __ldg(gmf + (size_t)sOwn[0] * NF);
+      // 16-edge chunks, double-buffered: the gathers of chunk c+1 are in flight while chunk c is scaled, packed
+      // and stored; the first chunk is issued before the operand buffer is even free
+      auto gather16 = [&](float (&av)[16], int c16) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint4 m = sMeta2[c16 * 8 + u];
+          av[2 * u] = __ldg(af + m.x);
+          av[2 * u + 1] = __ldg(af + m.z);
+        }
+      };
+      auto emit16 = [&](float (&av)[16], int c16) {
+        const uint32_t bits = (sMask[c16 >> 1] >> ((c16 & 1) * 16)) & 0xffffu;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (((bits >> (8 * q)) & 0xffu) == 0u) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) av[q * 8 + u] *= gm;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if ((bits >> (8 * q + u)) & 1u) gm = __ldg(gmf + (size_t)sOwn[c16 * 16 + q * 8 + u] * NF);
+              av[q * 8 + u] *= gm;
+            }
+          }
+          const int chunk = c16 * 2 + q;
+          *reinterpret_cast<uint4*>(sOp + (chunk >> 3) * (128 * 128) + sw128_off(f, chunk & 7)) =
+              make_uint4(pack_half2(av[q * 8], av[q * 8 + 1]), pack_half2(av[q * 8 + 2], av[q * 8 + 3]),
+                         pack_half2(av[q * 8 + 4], av[q * 8 + 5]), pack_half2(av[q * 8 + 6], av[q * 8 + 7]));
+        }
+      };
+      float xa[16], xb[16];
+      gather16(xa, 0);
+      mbar_wait_guard(bar(C_OP_EMPTY + g), ph ^ 1);
+      trace_stamp(2 + g, i, 1, f == 0);
+#pragma unroll 1
+      for (int c16 = 0; c16 < 8; c16 += 2) {
+        gather16(xb, c16 + 1);
+        emit16(xa, c16);
+        if (c16 + 2 < 8) gather16(xa, c16 + 2);
+        emit16(xb, c16 + 1);
+      }
+      fence_async_smem();
+      mbar_arrive(bar(C_GW_FULL + g));
+      mbar_arrive(bar(C_META_EMPTY + ms));
+      trace_stamp(2 + g, i, 2, f == 0);
+      phaseA(i);
+    }
+  } else if (warp < 16) {
+    // =========================================================== T (thread = feature j)
+    const int j = (warp & 3) * 32 + lane;
+    const int wq = warp & 3;
+    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
+    const float bias = sBias[j];
     auto phaseB = [&](int i) {
       const int s = i & 1, ms = i & (META_STAGES - 1);
       const uint32_t ph = (i >> 1) & 1;
-      const uint8_t* sT = smem + BO_ST + s * (2 * 128 * 128);
-      uint8_t* sOp = smem + BO_OP + s * (2 * 128 * 128);
+      // g_t overwrites t IN PLACE in the stash (same thread, same address), so the gW0 buffer sOp[s] is free as
+      // soon as MMA3 has read it and the gather warps never wait for MMA4
+      uint8_t* sT = smem + BO_ST + s * (2 * 128 * 128);
       const uint4* sMeta2 = reinterpret_cast<const uint4*>(smem + BO_META + ms * TILE * 8);
-      float* red = reinterpret_cast<float*>(smem + BO_RED + s * (4 * TILE * 4));
+      const int q4 = i & (D4_STAGES - 1);
+      float* red = reinterpret_cast<float*>(smem + BO_RED + q4 * (4 * TILE * 4));
+      trace_stamp(5, i, 0, j == 0);
+      mbar_wait_guard(bar(C_ST_FULL + s), ph);     // t of this tile written by the gather/tanh group
       mbar_wait_guard(bar(C_D3_FULL + s), ph);
-      if (kExact) mbar_wait_guard(bar(C_D4_EMPTY + s), ph ^ 1);  // e4(i-2) has read sRed[s]
+      if (kExact) mbar_wait_guard(bar(C_D4_EMPTY + q4), ((i / D4_STAGES) & 1) ^ 1);  // e4(i-4) has read sRed[q4]
+      trace_stamp(5, i, 1, j == 0);
       fence_after_sync();
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -563,7 +620,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
             p[u] = pack_half2(__uint_as_float(m.y) * d0 * fmaf(-tt.x, tt.x, 1.f),
                               __uint_as_float(m.w) * d1 * fmaf(-tt.y, tt.y, 1.f));
           }
-          *reinterpret_cast<uint4*>(sOp + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7)) =
+          *reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7)) =
               make_uint4(p[0], p[1], p[2], p[3]);
         }
         if (kExact) {
@@ -585,12 +642,9 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       fence_async_smem();
       mbar_arrive(bar(C_GT_FULL + s));
       mbar_arrive(bar(C_META_EMPTY + ms));
+      trace_stamp(5, i, 2, j == 0);
     };
-    if (n_my > 0) phaseA(0);
-    for (int i = 0; i < n_my; ++i) {
-      if (i + 1 < n_my) phaseA(i + 1);
-      phaseB(i);
-    }
+    for (int i = 0; i < n_my; ++i) phaseB(i);
   } else {
     // =========================================================== M: MMA issuer
     if (lane == 0 && n_my > 0) {
@@ -603,8 +657,10 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       auto issue1 = [&](int i) {
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
+        trace_stamp(6, i, 0, true);
         mbar_wait_guard(bar(C_RBF_FULL + s), ph);
         mbar_wait_guard(bar(C_D3_EMPTY + s), ph ^ 1);  // D13[s] drained by phaseB(i-2)
+        trace_stamp(6, i, 1, true);
         fence_after_sync();
         const uint64_t dB1 = smem_desc_sw128(sbase + BO_RBF + s * (128 * 128), 16, 1024);
 #pragma unroll
@@ -615,34 +671,43 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       auto issue3 = [&](int i) {
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
+        trace_stamp(7, i, 0, true);
         mbar_wait_guard(bar(C_GW_FULL + s), ph);
+        trace_stamp(7, i, 2, true);
         mbar_wait_guard(bar(C_D1_EMPTY + s), ph);  // phaseA(i) has drained D1 from D13[s]
+        trace_stamp(7, i, 1, true);
         fence_after_sync();
         const uint64_t dB3 = smem_desc_sw128(sbase + BO_OP + s * (2 * 128 * 128), 128 * 128, 1024);
 #pragma unroll
         for (int k = 0; k < NF / 16; ++k)
           mma_f16(tmem + s * 128, dA3 + (uint64_t)(k * (2048 / 16)), dB3 + (uint64_t)(k * (2048 / 16)), IDESC3, k > 0);
+        mma_commit(bar(C_OP_EMPTY + s));
         mma_commit(bar(C_D3_FULL + s));
       };
       auto issue4 = [&](int i) {
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
+        const int q4 = i & (D4_STAGES - 1);
+        trace_stamp(8, i, 0, true);
         mbar_wait_guard(bar(C_GT_FULL + s), ph);
-        mbar_wait_guard(bar(C_D4_EMPTY + s), ph ^ 1);
+        mbar_wait_guard(bar(C_D4_EMPTY + q4), ((i / D4_STAGES) & 1) ^ 1);
+        trace_stamp(8, i, 1, true);
         fence_after_sync();
-        const uint64_t dA4 = smem_desc_sw128(sbase + BO_OP + s * (2 * 128 * 128), 128 * 128, 1024);
+        const uint64_t dA4 = smem_desc_sw128(sbase + BO_ST + s * (2 * 128 * 128), 128 * 128, 1024);
 #pragma unroll
         for (int k = 0; k < NF / 16; ++k)
-          mma_f16(tmem + 256 + s * 64, dA4 + (uint64_t)(k * (2048 / 16)), dB4 + (uint64_t)(k * (2048 / 16)), IDESC4,
+          mma_f16(tmem + 256 + q4 * 64, dA4 + (uint64_t)(k * (2048 / 16)), dB4 + (uint64_t)(k * (2048 / 16)), IDESC4,
                   k > 0);
-        mma_commit(bar(C_OP_EMPTY + s));
-        mma_commit(bar(C_D4_FULL + s));
+        mma_commit(bar(C_ST_EMPTY + s));
+        mma_commit(bar(C_D4_FULL + q4));
       };
       issue1(0);
       for (int i = 0; i < n_my; ++i) {
+        // order matters: the issuer blocks in program order, so MMA4(i-1) (inputs ready early, releases the
+        // stash for the next tanh phase) must not queue behind MMA3(i), which waits for the gather warps
         if (i + 1 < n_my) issue1(i + 1);
-        issue3(i);
         if (i >= 1) issue4(i - 1);
+        issue3(i);
       }
       issue4(n_my - 1);
     }
@@ -709,5 +774,12 @@ extern "C" int fmd_filter_cfconv_bwd2(const float* dist, const int32_t* edge_own
                                             (const __half*)bf0_h, (const __half*)wf1_h, centers, num_rbf, gamma, rc, a,
                                             g_m, g_d, accumulate);
   FMD_CHECK_LAUNCH();
+  return FMD_OK;
+}
+
+// tools only: enable/disable the role timeline trace of the pipelined kernels (buffer: 9 * 64 * 3 uint64)
+extern "C" int fmd_debug_set_trace(void* device_buffer) {
+  unsigned long long* p = (unsigned long long*)device_buffer;
+  FMD_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
   return FMD_OK;
 }

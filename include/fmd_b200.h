@@ -185,6 +185,11 @@ int fmd_filter_cfconv_bwd2(const float* dist, const int32_t* edge_owner, const i
                            const float* centers, int num_rbf, float gamma, float rc, const float* a, const float* g_m,
                            int n_feat, float* g_d, int accumulate, int exact_cutoff_grad, void* stream);
 
+/* tools only (scripts/trace_roles.py): when device_buffer != NULL, CTA 0 of the pipelined tensor-core kernels
+ * records clock64() stamps {wait start, work start, end} per warp role and tile into
+ * uint64 trace[9 roles][64 tiles][3]; NULL switches the trace off. Not used on the step path. */
+int fmd_debug_set_trace(void* device_buffer);
+
 /* ---------------------------------------------------------------- dense layers -------------- */
 
 /* replaces: fused_tanh_linear (kernels/cfconv_kernels.py:1758-1941), fused_linear_tanh_fp16 (:644-760),

@@ -27,6 +27,7 @@ ROOT = os.path.dirname(HERE)
 for k in ("MLCG_USE_TRITON_MESSAGE_PASSING", "MLCG_USE_FUSED_RBF", "MLCG_USE_FUSED_TANH_LINEAR",
           "MLCG_USE_CSR", "MLCG_USE_SRC_CSR_GRAD_X"):
     os.environ[k] = "0"
+sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(HERE, "shims"))
 sys.path.insert(1, "/root/reference/src")
 
@@ -278,9 +279,41 @@ def golden_known_answers(fname):
     print(fname, "ok")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--stats" not in sys.argv:
     golden_known_answers("known_answers.npz")
     system, model, schnet, configs = golden_static("schnet_n54_b4.npz", 4, 54, 0, 128, 128, 50, 3, (128, 64), 30.0)
     golden_langevin(system, model, schnet, configs, "langevin_n54_b4.npz", n_steps=10)
     golden_static("schnet_n24_b3_l2.npz", 3, 24, 3, 64, 64, 20, 2, (32,), 10.0, bias_scale=0.2)
     golden_pt("pt_n24.npz")
+
+
+def golden_stats(fname, n_steps=10000, n_mols=8, save_interval=10):
+    """Trajectory statistics of the UNMODIFIED reference (CPU path) over 10^4 Langevin steps: kinetic
+    energy (temperature), RMSD from the start structure, radius of gyration, potential energy.  The GPU tests
+    compare the fused engine's own 10^4-step trajectories with these distributions (north_star)."""
+    import tempfile
+    system = syn.synthetic_system(n_mols, 54, seed=0, target_degree=30.0)
+    model, schnet, configs = build_reference(system, 128, 128, 50, 3, (128, 64), 0)
+    tmp = tempfile.mkdtemp()
+    torch.manual_seed(4321)
+    sim = LangevinSimulation(friction=1.0, dt=0.004, n_timesteps=n_steps, save_interval=save_interval,
+                             export_interval=n_steps, save_energies=True, random_seed=2024, device="cpu",
+                             dtype="single", filename="s", output_dir=tmp, specialize_priors=True,
+                             compile_model=False, gptq=None)
+    sim.attach_model_and_configurations(model, configs, beta=1.67)
+    sim.simulate()
+    x = np.load(os.path.join(tmp, "s_coords_0000.npy"))            # [B, frames, n, 3]
+    ke = np.load(os.path.join(tmp, "s_kineticenergy_0000.npy"))    # [B, frames]
+    pe = np.load(os.path.join(tmp, "s_potential_0000.npy"))
+    x0 = system["pos"][:n_mols]
+    from tests_helpers_kabsch import kabsch_rmsd, radius_of_gyration
+    rmsd = np.stack([[kabsch_rmsd(x[b, f], x0[b]) for f in range(x.shape[1])] for b in range(n_mols)])
+    rg = radius_of_gyration(x)
+    arrs = {"ke": ke, "pe": pe, "rmsd": rmsd, "rg": rg, "params": np.array([0.004, 1.0, 1.67, n_steps, save_interval]),
+            "n_mols": np.array(n_mols)}
+    np.savez_compressed(os.path.join(OUT, fname), **arrs)
+    print(fname, "KE mean", ke[:, 100:].mean(), "expected", 1.5 * 54 / 1.67, "rmsd end", rmsd[:, -1].mean())
+
+
+if __name__ == "__main__" and "--stats" in sys.argv:
+    golden_stats("stats_n54_10k.npz")
