@@ -120,3 +120,55 @@ def test_pt_simulation_fused_engine(tmp_path):
     assert np.load(tmp_path / "pt_acceptance_0002.npy").sum() == 5 * 4
     assert np.load(tmp_path / "pt_coords_0001.npy").shape == (12, 10, 54, 3)
     assert np.isfinite(np.load(tmp_path / "pt_kineticenergy_0001.npy")).all()
+
+
+@pytest.mark.parametrize("gptq", ["w16a16", None])
+def test_trajectory_statistics_vs_reference_10k_steps(gptq):
+    """north_star: temperature and RMSD statistics agree with the reference over 10^4-step trajectories.
+    Reference side: tests/golden/stats_n54_10k.npz, 8 molecules x 10^4 BAOAB steps of the UNMODIFIED reference
+    (oracle/make_golden.py --stats).  Ours: the same model, 64 replicas (8 copies of each start structure), own
+    Philox noise -> only distributions can agree; tolerances are a few standard errors of the reference sample."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    from tests_helpers_kabsch import kabsch_rmsd, radius_of_gyration
+    from flashmd import synthetic
+    from flashmd.simulation import LangevinSimulation
+    ref = load_golden("stats_n54_10k.npz")
+    g = load_golden("schnet_n54_b4.npz")
+    n_ref = int(ref["n_mols"])
+    system = synthetic.synthetic_system(n_ref, 54, seed=0, target_degree=30.0)
+    # the statistics run used the same seeded weights / bead types / prior tables as the golden model, on the
+    # 8-molecule synthetic system (its own start structures and tuned cutoff)
+    g = dict(g)
+    g["sys.pos"], g["sys.cutoff"] = system["pos"], np.float64(system["cutoff"])
+    assert np.array_equal(system["atom_types"], g["sys.atom_types"])
+    model, _, configs0 = dropin_model_from_golden(g)
+    configs = [deepcopy(configs0[b]) for rep in range(8) for b in range(n_ref)]
+    dt, friction, beta, n_steps, save_interval = (float(v) for v in ref["params"])
+    sim = LangevinSimulation(friction=friction, dt=dt, n_timesteps=int(n_steps), save_interval=int(save_interval),
+                             save_energies=True, random_seed=99, device=DEV, gptq=gptq)
+    sim.attach_model_and_configurations(model, configs, beta=beta)
+    sim.simulate()
+    assert sim.get_throughput_metrics()["path"] == "fused-engine"
+    x, ke, pe = sim.simulated_coords, sim.simulated_kinetic_energies, sim.simulated_potential
+    assert x.shape == (64, 1000, 54, 3) and np.isfinite(x).all()
+    burn = 100
+    # --- temperature: <KE> and its fluctuation (equipartition: mean 3N/2beta, relative std sqrt(2/(3N)))
+    ke_ref, ke_our = ref["ke"][:, burn:], ke[:, burn:]
+    assert abs(ke_our.mean() / ke_ref.mean() - 1.0) < 0.01, (ke_our.mean(), ke_ref.mean())
+    # canonical fluctuation: std = mean * sqrt(2 / (3 N)); the 8-molecule reference sample sits 11 % above it
+    canon = ke_ref.mean() * np.sqrt(2.0 / (3 * 54))
+    assert abs(ke_our.std() / canon - 1.0) < 0.05, (ke_our.std(), canon)
+    assert abs(ke_our.std() / ke_ref.std() - 1.0) < 0.15, (ke_our.std(), ke_ref.std())
+    # --- potential energy level
+    se = ref["pe"][:, burn:].mean(axis=1).std() / np.sqrt(n_ref)
+    assert abs(pe[:, burn:].mean() - ref["pe"][:, burn:].mean()) < 5 * se + 0.01 * abs(ref["pe"][:, burn:].mean())
+    # --- structure: RMSD from the start structure at several times, radius of gyration
+    x0 = system["pos"]
+    for frame in (99, 299, 599, 999):
+        ours = np.array([kabsch_rmsd(x[i, frame], x0[i % n_ref]) for i in range(64)])
+        r = ref["rmsd"][:, frame]
+        tol = 4.0 * r.std() / np.sqrt(n_ref) + 0.05 * r.mean()
+        assert abs(ours.mean() - r.mean()) < tol, (frame, ours.mean(), r.mean(), tol)
+    rg_our, rg_ref = radius_of_gyration(x[:, burn:]), ref["rg"][:, burn:]
+    assert abs(rg_our.mean() / rg_ref.mean() - 1.0) < 0.05, (rg_our.mean(), rg_ref.mean())
