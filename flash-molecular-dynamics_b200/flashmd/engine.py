@@ -81,6 +81,7 @@ class SchNetWeights:
                 wp = torch.zeros((self.filters, 64), dtype=torch.float16, device=dev)
                 wp[:, :self.num_rbf] = k[f"b{l}.f0_w.h"]
                 k[f"b{l}.f0_w.hp"] = wp.contiguous()
+        k["emb_lin1"] = (k["embedding"].double() @ k["b0.lin1_w"].double().t()).float().contiguous()
         self.k = k
         # [K,N] weight tensor -> the same matrix stored [N,K] (its transpose twin), for fmd_linear_tc's fast staging
         self.twin = {}
@@ -332,7 +333,12 @@ class ForceField:
         tanh_f = L.ACT_TANH_CLAMPED if w16 else L.ACT_TANH
         sfx = ".h" if w16 else ""
         for l in range(nb):
-            self._lin(self.h[l], k[f"b{l}.lin1_wT"], None, self.a[l])
+            if l == 0:
+                # a_0 = Emb[types] W1^T = (Emb W1^T)[types]: the [n_types, F] product is precomputed once
+                L.call("fmd_embedding", L.ptr(k["emb_lin1"]), L.ptr(self.types), 4, self.N, w.filters, L.ptr(self.a[0]), st)
+                self._n += 1
+            else:
+                self._lin(self.h[l], k[f"b{l}.lin1_wT"], None, self.a[l])
             if tc:
                 self._filter_cfconv(l, self.a[l], self.m)
             else:
@@ -370,13 +376,15 @@ class ForceField:
             self._lin(gh_cur, k[f"b{l}.lin_w"], None, self.g_c, aux=self.c[l])
             self._lin(self.g_c, k[f"b{l}.lin2_w"], None, self.g_m)
             if tc:
-                self._filter_cfconv(l, self.g_m, self.g_a)
                 self._filter_cfconv_bwd(l, self.a[l], self.g_m)
-                self._lin(self.g_a, k[f"b{l}.lin1_w"], None, gh_nxt, res=gh_cur)
-                gh_cur, gh_nxt = gh_nxt, gh_cur
+                if l > 0:      # dE/dh_0 (the embedding gradient) is not needed for forces: skip g_a / g_h of block 0
+                    self._filter_cfconv(l, self.g_m, self.g_a)
+                    self._lin(self.g_a, k[f"b{l}.lin1_w"], None, gh_nxt, res=gh_cur)
+                    gh_cur, gh_nxt = gh_nxt, gh_cur
                 continue
             # m[i] = sum_{e in seg(i)} a[dst_e] W_e C_e
-            self._cfconv(self.g_m, self.W[l], self.g_a)
+            if l > 0:
+                self._cfconv(self.g_m, self.W[l], self.g_a)
             L.call("fmd_cfconv_grad_filter", L.ptr(self.g_m), L.ptr(self.a[l]), L.ptr(self.dist), L.ptr(self.src),
                    L.ptr(self.dst), 4, self.cap, L.ptr(ned), w.filters, w.cutoff, L.ptr(self.gW), L.dt_code(self.gW),
                    L.ptr(self.W[l]) if self.exact else None, L.dt_code(self.W[l]),
@@ -388,9 +396,10 @@ class ForceField:
             L.call("fmd_rbf_bwd", L.ptr(self.dist), L.ptr(self.g_rbf), None, self.cap, L.ptr(ned), L.ptr(w.centers),
                    w.num_rbf, w.gamma, w.cutoff, L.ptr(self.g_d), 1, st)
             self._n += 1
-            # g_h <- g_h + g_a @ lin1_w[f,h]
-            self._lin(self.g_a, k[f"b{l}.lin1_w"], None, gh_nxt, res=gh_cur)
-            gh_cur, gh_nxt = gh_nxt, gh_cur
+            # g_h <- g_h + g_a @ lin1_w[f,h]   (not needed below block 0: dE/dh_0 does not enter the forces)
+            if l > 0:
+                self._lin(self.g_a, k[f"b{l}.lin1_w"], None, gh_nxt, res=gh_cur)
+                gh_cur, gh_nxt = gh_nxt, gh_cur
         L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(self.seg_ptr), L.ptr(self.dst), L.ptr(self.rev),
                L.ptr(self.dist), L.ptr(self.g_d), self.N, self.cap, 1.0, L.ptr(self.forces), 0, st)
         self._n += 1

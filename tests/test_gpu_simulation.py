@@ -155,7 +155,10 @@ def test_trajectory_statistics_vs_reference_10k_steps(gptq):
     burn = 100
     # --- temperature: <KE> and its fluctuation (equipartition: mean 3N/2beta, relative std sqrt(2/(3N)))
     ke_ref, ke_our = ref["ke"][:, burn:], ke[:, burn:]
-    assert abs(ke_our.mean() / ke_ref.mean() - 1.0) < 0.01, (ke_our.mean(), ke_ref.mean())
+    # equipartition 3N/(2 beta) = 48.50; the 8-molecule reference sample (48.83) carries ~0.7 % standard error
+    # (velocity autocorrelation ~ 1/friction = 25 saved frames), ours 64 molecules
+    assert abs(ke_our.mean() / (1.5 * 54 / beta) - 1.0) < 0.01, ke_our.mean()
+    assert abs(ke_our.mean() / ke_ref.mean() - 1.0) < 0.025, (ke_our.mean(), ke_ref.mean())
     # canonical fluctuation: std = mean * sqrt(2 / (3 N)); the 8-molecule reference sample sits 11 % above it
     canon = ke_ref.mean() * np.sqrt(2.0 / (3 * 54))
     assert abs(ke_our.std() / canon - 1.0) < 0.05, (ke_our.std(), canon)
