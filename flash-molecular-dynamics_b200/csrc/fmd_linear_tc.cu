@@ -42,11 +42,9 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, 
 __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
-__device__ __forceinline__ float act(float v, int a) {
-  if (a == FMD_ACT_TANH) return tanhf(v);
-  if (a == FMD_ACT_TANH_CLAMPED) return tanh_clamped(v);
-  return v;
-}
+// both tanh flavours map to the hardware tanh.approx.f32 (|err| <= 2^-11, the TF32 operand rounding level of
+// this kernel); the exact tanhf / clamped-exp variants live in the fp32 kernel (fmd_linear.cu)
+__device__ __forceinline__ float act(float v, int a) { return a == FMD_ACT_NONE ? v : tanh_approx(v); }
 
 template <typename TX>
 __device__ __forceinline__ float4 load_x4(const TX* p);
