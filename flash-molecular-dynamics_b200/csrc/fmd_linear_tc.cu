@@ -6,7 +6,8 @@
 // W16A16 output network (fp16 operands, fp32 accumulate: models/gptq.py:266-306) is reproduced exactly.
 // The fp32 parity path (1e-5) never comes here: it stays on the true-fp32 FMA kernel of fmd_linear.cu.
 //
-// One persistent CTA per SM, 128 threads.  The weight matrix is staged once per CTA (transposed on the
+// One persistent CTA per SM, two 128-thread groups that run the same code on two row tiles concurrently (their
+// load / MMA / epilogue phases overlap; the weights are shared).  The weight matrix is staged once per CTA (transposed on the
 // fly into the K-major B operand); per 128-row tile the CTA stages pro(X) as the K-major A operand (round-to-nearest TF32),
 // one thread issues K/8 MMAs (both operands K-major), and thread r drains row r of the accumulator through the epilogue.
 #include "fmd_tc.cuh"
@@ -17,9 +18,11 @@ using namespace fmd::tc;
 namespace {
 
 constexpr int LT_TILE = 128;
-constexpr uint32_t LO_A = 0;                  // up to 4 K-blocks x [128 rows][128 B] = 64 KB
-constexpr uint32_t LO_B = 64 * 1024;          // up to 4 N-blocks x [128 k][128 B]   = 64 KB
-constexpr uint32_t LO_BIAS = 128 * 1024;      // 128 floats
+constexpr int LT_GROUPS = 2;                  // two 128-thread groups per CTA work on two row tiles concurrently
+constexpr int LT_THREADS = LT_TILE * LT_GROUPS;
+constexpr uint32_t LO_A = 0;                  // per group: up to 4 K-blocks x [128 rows][128 B] = 64 KB
+constexpr uint32_t LO_B = 2 * 64 * 1024;      // shared: up to 4 K-blocks x [128 n][128 B]     = 64 KB
+constexpr uint32_t LO_BIAS = 3 * 64 * 1024;   // 128 floats
 constexpr uint32_t LO_BAR = LO_BIAS + 512;
 constexpr uint32_t LT_SMEM = LO_BAR + 32;
 constexpr uint32_t LT_SMEM_ALLOC = LT_SMEM + 1024;
@@ -54,7 +57,7 @@ template <>
 __device__ __forceinline__ float4 load_x4<__half>(const __half* p) { return load4(p); }
 
 template <typename TX, typename TW, typename TY>
-__global__ void __launch_bounds__(LT_TILE, 1)
+__global__ void __launch_bounds__(LT_THREADS, 1)
 linear_tc_kernel(const TX* __restrict__ X, const TW* __restrict__ W, const TW* __restrict__ bias, TY* __restrict__ Y,
                  int M, int N, int K, const int32_t* __restrict__ m_dev, int pro_act, int x_round_f16, int epi_act,
                  const void* __restrict__ aux, int auxdt, const float* __restrict__ res, int w_nk) {
@@ -62,10 +65,15 @@ linear_tc_kernel(const TX* __restrict__ X, const TW* __restrict__ W, const TW* _
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   const uint32_t sbase = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid_all = threadIdx.x, warp_all = tid_all >> 5;
+  const int group = tid_all >> 7;               // 0 / 1
+  const int tid = tid_all & (LT_TILE - 1);      // thread index inside the group == accumulator row
+  const int warp = tid >> 5;                    // == warp_all % 4: the TMEM lane quarter this warp may read
   float* sBias = reinterpret_cast<float*>(smem + LO_BIAS);
-  const uint32_t bar = sbase + LO_BAR;
+  const uint32_t bar = sbase + LO_BAR + 8u * group;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + LO_BAR + 16);
+  uint8_t* sA = smem + LO_A + group * (64 * 1024);
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(LT_TILE) : "memory"); };
   if (m_dev) M = min(M, *m_dev);
   const int n_tiles = (M + LT_TILE - 1) / LT_TILE;
   const int kc = K / 4;  // 16-byte chunks per X row
@@ -75,17 +83,17 @@ linear_tc_kernel(const TX* __restrict__ X, const TW* __restrict__ W, const TW* _
     // W given as [N][K] (nn.Linear.weight layout): 16-byte chunks, coalesced, 8 in flight
     const int kc_shift = (K == 128) ? 5 : 4;
     const int total = N << kc_shift;
-    for (int base = 0; base < total; base += LT_TILE * 8) {
+    for (int base = 0; base < total; base += LT_THREADS * 8) {
       float4 v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int idx = base + u * LT_TILE + tid;
+        const int idx = base + u * LT_THREADS + tid_all;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (idx < total) v[u] = load4(W + (size_t)idx * 4);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int idx = base + u * LT_TILE + tid;
+        const int idx = base + u * LT_THREADS + tid_all;
         const int n = idx >> kc_shift, c = idx & (kc - 1);
         float4 t = v[u];
         t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
@@ -96,18 +104,18 @@ linear_tc_kernel(const TX* __restrict__ X, const TW* __restrict__ W, const TW* _
     // W given as [K][N]: task = (n, 4 consecutive k), the scalar loads are coalesced across threads (n fastest)
     const int n_shift = (N == 128) ? 7 : 6;
     const int total = (K >> 2) * N;
-    for (int base = 0; base < total; base += LT_TILE * 4) {
+    for (int base = 0; base < total; base += LT_THREADS * 4) {
       float w[4][4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * LT_TILE + tid;
+        const int idx = base + u * LT_THREADS + tid_all;
         const int n = idx & (N - 1), kq = idx >> n_shift;
 #pragma unroll
         for (int q = 0; q < 4; ++q) w[u][q] = idx < total ? to_f32<TW>(W[(size_t)(kq * 4 + q) * N + n]) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * LT_TILE + tid;
+        const int idx = base + u * LT_THREADS + tid_all;
         const int n = idx & (N - 1), kq = idx >> n_shift;
         if (idx < total)
           *reinterpret_cast<float4*>(smem + LO_B + (kq >> 3) * (N * 128) + sw128_off(n, kq & 7)) =
@@ -115,28 +123,30 @@ linear_tc_kernel(const TX* __restrict__ X, const TW* __restrict__ W, const TW* _
       }
     }
   }
-  if (tid < N) sBias[tid] = bias ? to_f32<TW>(bias[tid]) : 0.f;
-  if (tid == 0) {
-    mbar_init(bar, 1);
+  if (tid_all < N) sBias[tid_all] = bias ? to_f32<TW>(bias[tid_all]) : 0.f;
+  if (tid_all == 0) {
+    mbar_init(sbase + LO_BAR, 1);
+    mbar_init(sbase + LO_BAR + 8, 1);
     fence_mbar_init();
   }
-  if (warp == 0) {
+  if (warp_all == 0) {
     __syncwarp();
-    tmem_alloc(sbase + LO_BAR + 16, 128);
+    tmem_alloc(sbase + LO_BAR + 16, 256);
   }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem = tmem_base + group * 128;
   const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
   const uint32_t idesc = idesc_tf32(128, N, 0, 0);
-  const uint64_t dA = smem_desc_sw128(sbase + LO_A, 16, 1024);
+  const uint64_t dA = smem_desc_sw128(sbase + LO_A + group * (64 * 1024), 16, 1024);
   const uint64_t dB = smem_desc_sw128(sbase + LO_B, 16, 1024);
   const uint32_t b_kblock = (uint32_t)(N * 128 / 16);
 
   uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  for (int tile = blockIdx.x * LT_GROUPS + group; tile < n_tiles; tile += gridDim.x * LT_GROUPS, ++it) {
     const int m0 = tile * LT_TILE;
     // ---- stage pro(X) tile: [128 rows][K] fp32, K-block kb (32 floats) at kb * 16 KB; 8 loads in flight per thread
     {
@@ -162,13 +172,13 @@ linear_tc_kernel(const TX* __restrict__ X, const TW* __restrict__ W, const TW* _
           }
           if (pro_act) { t.x = act(t.x, pro_act); t.y = act(t.y, pro_act); t.z = act(t.z, pro_act); t.w = act(t.w, pro_act); }
           t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
-          *reinterpret_cast<float4*>(smem + LO_A + (c >> 3) * (128 * 128) + sw128_off(r, c & 7)) = t;
+          *reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(r, c & 7)) = t;
         }
       }
     }
     fence_async_smem();
     fence_before_sync();  // previous tile's accumulator reads are complete
-    __syncthreads();
+    group_sync();
     if (tid == 0) {
       fence_after_sync();
       for (int k = 0; k < K / 8; ++k)
@@ -212,7 +222,7 @@ linear_tc_kernel(const TX* __restrict__ X, const TW* __restrict__ W, const TW* _
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp_all == 0) tmem_dealloc(tmem_base, 256);
 }
 
 template <typename TX, typename TW, typename TY>
@@ -224,9 +234,9 @@ int launch_tc(const void* X, const void* W, const void* bias, void* Y, int M, in
     FMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM_ALLOC));
     attr_done = true;
   }
-  const int tiles = fmd_div_up(M, LT_TILE);
-  const int grid = tiles < fmd_num_sms() ? tiles : fmd_num_sms();
-  kern<<<grid, LT_TILE, LT_SMEM_ALLOC, st>>>((const TX*)X, (const TW*)W, (const TW*)bias, (TY*)Y, M, N, K, m_dev,
+  const int pairs = fmd_div_up(fmd_div_up(M, LT_TILE), LT_GROUPS);
+  const int grid = pairs < fmd_num_sms() ? pairs : fmd_num_sms();
+  kern<<<grid, LT_THREADS, LT_SMEM_ALLOC, st>>>((const TX*)X, (const TW*)W, (const TW*)bias, (TY*)Y, M, N, K, m_dev,
                                              pro_act, x_round, epi_act, aux, auxdt, res, w_nk);
   return FMD_OK;
 }
