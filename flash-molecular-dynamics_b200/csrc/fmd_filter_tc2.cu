@@ -127,8 +127,10 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       const float cut = valid ? cosine_cutoff_fast(d, pi_over_rc, rc) : 0.f;
       // segment boundary inside the tile: this edge starts a new owner's run (tile-local edge 0 is the "head")
       const uint32_t bmask = __ballot_sync(0xffffffffu, valid && tid > 0 && own != prev);
+      trace_stamp(0, i, 0, tid == 0);
       mbar_wait_guard(bar(B_META_EMPTY + ms), mph ^ 1);
       mbar_wait_guard(bar(B_RBF_EMPTY + s), ph ^ 1);
+      trace_stamp(0, i, 1, tid == 0);
       reinterpret_cast<uint32_t*>(smem + O_XOFF + ms * TILE * 4)[tid] = (uint32_t)nb * (uint32_t)NF;
       reinterpret_cast<float*>(smem + O_CUT + ms * TILE * 4)[tid] = cut;
       reinterpret_cast<int*>(smem + O_OWN + ms * TILE * 4)[tid] = own;
@@ -138,6 +140,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       write_rbf_row_fast(smem + O_RBF + s * (128 * 128), sCen, tid, d, cut, g2);
       fence_async_smem();
       mbar_arrive(bar(B_RBF_FULL + s));
+      trace_stamp(0, i, 2, tid == 0);
     }
   } else if (warp == 4) {
     // =========================================================== M: MMA issuer (one thread)
@@ -149,8 +152,10 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       auto issue1 = [&](int i) {
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
+        trace_stamp(4, i, 0, true);
         mbar_wait_guard(bar(B_RBF_FULL + s), ph);
         mbar_wait_guard(bar(B_D1_EMPTY + s), ph ^ 1);
+        trace_stamp(4, i, 1, true);
         fence_after_sync();
         const uint64_t dB1 = smem_desc_sw128(sbase + O_RBF + s * (128 * 128), 16, 1024);
 #pragma unroll
@@ -161,8 +166,10 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       auto issue2 = [&](int i) {
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
+        trace_stamp(5, i, 0, true);
         mbar_wait_guard(bar(B_TT_FULL + s), ph);
         mbar_wait_guard(bar(B_D2_EMPTY + s), ph ^ 1);
+        trace_stamp(5, i, 1, true);
         fence_after_sync();
         const uint64_t dB2 = smem_desc_sw128(sbase + O_TT + s * (2 * 128 * 128), 128 * 128, 1024);
 #pragma unroll
@@ -186,8 +193,10 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
     for (int i = 0; i < n_my; ++i) {
       const int s = i & 1, ms = i & (META_STAGES - 1);
       const uint32_t ph = (i >> 1) & 1;
+      trace_stamp(1, i, 0, j == 0);
       mbar_wait_guard(bar(B_D1_FULL + s), ph);
       mbar_wait_guard(bar(B_TT_EMPTY + s), ph ^ 1);
+      trace_stamp(1, i, 1, j == 0);
       fence_after_sync();
       uint8_t* sTT = smem + O_TT + s * (2 * 128 * 128);
       const float4* sCut4 = reinterpret_cast<const float4*>(smem + O_CUT + ms * TILE * 4);
@@ -216,6 +225,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_arrive(bar(B_META_EMPTY + ms));
       fence_async_smem();
       mbar_arrive(bar(B_TT_FULL + s));
+      trace_stamp(1, i, 2, j == 0);
     }
   } else {
     // =========================================================== E0 / E1: epilogue (thread = feature f)
@@ -241,6 +251,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
           xv[4 * u + 3] = __ldg(xf + o.w);
         }
       };
+      trace_stamp(2 + g, i, 0, f == 0);
       mbar_wait_guard(bar(B_META_FULL + ms), mph);
       float xa[16], xb[16];
       gather16(xa, 0);
@@ -271,6 +282,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         }
       };
       mbar_wait_guard(bar(B_D2_FULL + g), ph);
+      trace_stamp(2 + g, i, 1, f == 0);
       fence_after_sync();
       const uint32_t d2 = tmem + 256 + g * 128 + lane_sel;
 #pragma unroll 1
@@ -289,6 +301,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_arrive(bar(B_D2_EMPTY + g));
       mbar_arrive(bar(B_META_EMPTY + ms));
       flush(0);
+      trace_stamp(2 + g, i, 2, f == 0);
     }
   }
   __syncthreads();

@@ -161,3 +161,16 @@ def test_cli_config1_cpu_disable_optim(tmp_path):
     assert c0.shape == c1.shape == (4, 2, 54, 3) and np.isfinite(c1).all()
     assert os.path.exists(tmp_path / "run_config.yaml") and os.path.exists(tmp_path / "run_log.txt")
     assert '"path": "module"' in r.stdout
+
+
+def test_nve_simulation_module_path_conserves_energy():
+    from flashmd.simulation import NVESimulation
+    g = load_golden("schnet_n24_b3_l2.npz")
+    model, _, configs = dropin_model_from_golden(g)
+    torch.manual_seed(3)
+    sim = NVESimulation(dt=0.001, n_timesteps=200, save_interval=10, save_energies=True, random_seed=1, device="cpu",
+                        dtype="double", gptq=None)
+    sim.attach_model_and_configurations(model, configs, beta=1.67)
+    sim.simulate()
+    e_tot = sim.simulated_potential + sim.simulated_kinetic_energies
+    assert np.abs(e_tot - e_tot[:, :1]).max() / sim.simulated_kinetic_energies.mean() < 2e-3

@@ -175,3 +175,24 @@ def test_trajectory_statistics_vs_reference_10k_steps(gptq):
         assert abs(ours.mean() - r.mean()) < tol, (frame, ours.mean(), r.mean(), tol)
     rg_our, rg_ref = radius_of_gyration(x[:, burn:]), ref["rg"][:, burn:]
     assert abs(rg_our.mean() / rg_ref.mean() - 1.0) < 0.05, (rg_our.mean(), rg_ref.mean())
+
+
+@pytest.mark.parametrize("gptq,tol", [(None, 2e-4), ("w16a16", 2e-3)])
+def test_nve_energy_conservation_fused_engine(gptq, tol):
+    """Velocity Verlet through the fused engine: total energy is conserved, which checks that the analytic
+    forces are the gradient of the energy the kernels report."""
+    from flashmd.simulation import NVESimulation
+    g = load_golden("schnet_n54_b4.npz")
+    model, _, configs = dropin_model_from_golden(g)
+    torch.manual_seed(3)
+    sim = NVESimulation(dt=0.001, n_timesteps=2000, save_interval=20, save_energies=True, random_seed=1, device=DEV,
+                        gptq=gptq)
+    sim.attach_model_and_configurations(model, configs, beta=1.67)
+    sim.simulate()
+    assert sim.get_throughput_metrics()["path"] == "fused-engine"
+    e_tot = sim.simulated_potential + sim.simulated_kinetic_energies      # [n_sims, frames]
+    ke_scale = sim.simulated_kinetic_energies.mean()
+    drift = np.abs(e_tot - e_tot[:, :1]).max() / ke_scale
+    assert drift < tol * 50, drift          # bounded fluctuation of the shadow Hamiltonian, no systematic drift
+    slope = np.abs(e_tot[:, -10:].mean(axis=1) - e_tot[:, :10].mean(axis=1)).max() / ke_scale
+    assert slope < tol * 25, slope
