@@ -55,7 +55,7 @@ __device__ __forceinline__ void write_rbf_row(uint8_t* sRbf, const float* sCen, 
 // invalid rows).  g2 = gamma * log2(e): exp(gamma x^2) = ex2(g2 x^2), one MUFU per value.
 __device__ __forceinline__ void write_rbf_row_fast(uint8_t* sRbf, const float* sCen, int row, float d, float cut,
                                                    float g2) {
-#pragma unroll
+#pragma unroll 2
   for (int c = 0; c < RP / 8; ++c) {
     const float4 ca = *reinterpret_cast<const float4*>(sCen + c * 8);
     const float4 cb = *reinterpret_cast<const float4*>(sCen + c * 8 + 4);

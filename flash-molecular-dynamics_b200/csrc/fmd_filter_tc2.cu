@@ -200,7 +200,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       fence_after_sync();
       uint8_t* sTT = smem + O_TT + s * (2 * 128 * 128);
       const float4* sCut4 = reinterpret_cast<const float4*>(smem + O_CUT + ms * TILE * 4);
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem + s * 128 + lane_sel + c * 32, r);
@@ -510,7 +510,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_wait_guard(bar(C_ST_EMPTY + s), ph ^ 1);   // MMA4(i-2) has consumed g_t from sT[s]
       trace_stamp(4, i, 1, f == 0);
       fence_after_sync();
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem + s * 128 + lane_sel + c * 32, r);
