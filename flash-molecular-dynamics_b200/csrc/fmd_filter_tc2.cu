@@ -18,6 +18,7 @@ using namespace fmd::filt;
 namespace {
 
 constexpr int NTHREADS = 17 * 32;
+constexpr int BWD_THREADS = 19 * 32;   // backward: three MMA-issuer warps (the register allocation granularity is 20 warps anyway)
 
 // Optional timeline trace (tools only; scripts/trace_roles.py): when set, CTA 0 records clock64() stamps
 // {wait start, work start, end} per role and tile into trace[role][tile < 64][3].
@@ -315,7 +316,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
 //   G0 warps 4-7   thread-per-feature, even tiles: row f of gW0^T = a[nbr,f] * g_m[owner,f]; then D1 -> t (stash)
 //   G1 warps 8-11  same for odd tiles
 //   T  warps 12-15 thread-per-feature: D3 -> g_t row (in place over t) + cut-term sums
-//   M  warp  16    MMA issue: D13[s] = Wf0.rbf^T ; D13[s] = Wf1^T.gW0^T ; D4[s] = g_t.Wf0
+//   M  warps 16-18 one MMA-issuer thread each: D13[s] = Wf0.rbf^T | D13[s] = Wf1^T.gW0^T | D4[q] = g_t.Wf0
 constexpr uint32_t BO_WF0 = 0;
 constexpr uint32_t BO_WF1 = BO_WF0 + 128 * 128;
 constexpr uint32_t BO_RBF = BO_WF1 + 2 * 128 * 128;          // 2 x 16 KB
@@ -340,7 +341,7 @@ constexpr int D4_STAGES = 4;   // D4 (64 columns) is quadruple-buffered so that 
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
 
 template <bool kExact>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restrict__ edge_owner,
                           const int32_t* __restrict__ edge_nbr, int capacity,
                           const int32_t* __restrict__ n_edges_dev, const __half* __restrict__ wf0,
@@ -542,47 +543,47 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       trace_stamp(2 + g, i, 0, f == 0);
       mbar_wait_guard(bar(C_META_FULL + ms), mph);
       float gm = __ldg(gmf + (size_t)sOwn[0] * NF);
-      // 16-edge chunks, double-buffered: the gathers of chunk c+1 are in flight while chunk c is scaled, packed
-      // and stored; the first chunk is issued before the operand buffer is even free
-      auto gather16 = [&](float (&av)[16], int c16) {
+      // Two half-tiles of 64 edges: all 64 row gathers of a half are in flight at once (the latency of the L2
+      // gathers is paid twice per tile instead of once per 16 rows: 8.6k -> ~4k cycles in the timeline trace); the
+      // first half is issued before the operand buffer is even free.
+      float av[64];
+      auto gather64 = [&](int h) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint4 m = sMeta2[c16 * 8 + u];
+        for (int u = 0; u < 32; ++u) {
+          const uint4 m = sMeta2[h * 32 + u];
           av[2 * u] = __ldg(af + m.x);
           av[2 * u + 1] = __ldg(af + m.z);
         }
       };
-      auto emit16 = [&](float (&av)[16], int c16) {
-        const uint32_t bits = (sMask[c16 >> 1] >> ((c16 & 1) * 16)) & 0xffffu;
+      auto emit64 = [&](int h) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (((bits >> (8 * q)) & 0xffu) == 0u) {
+        for (int w = 0; w < 2; ++w) {
+          const uint32_t bits = sMask[h * 2 + w];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) av[q * 8 + u] *= gm;
-          } else {
+          for (int q = 0; q < 4; ++q) {
+            float* v = av + w * 32 + q * 8;
+            if (((bits >> (8 * q)) & 0xffu) == 0u) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if ((bits >> (8 * q + u)) & 1u) gm = __ldg(gmf + (size_t)sOwn[c16 * 16 + q * 8 + u] * NF);
-              av[q * 8 + u] *= gm;
+              for (int u = 0; u < 8; ++u) v[u] *= gm;
+            } else {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                if ((bits >> (8 * q + u)) & 1u) gm = __ldg(gmf + (size_t)sOwn[h * 64 + w * 32 + q * 8 + u] * NF);
+                v[u] *= gm;
+              }
             }
+            const int chunk = h * 8 + w * 4 + q;
+            *reinterpret_cast<uint4*>(sOp + (chunk >> 3) * (128 * 128) + sw128_off(f, chunk & 7)) =
+                make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
           }
-          const int chunk = c16 * 2 + q;
-          *reinterpret_cast<uint4*>(sOp + (chunk >> 3) * (128 * 128) + sw128_off(f, chunk & 7)) =
-              make_uint4(pack_half2(av[q * 8], av[q * 8 + 1]), pack_half2(av[q * 8 + 2], av[q * 8 + 3]),
-                         pack_half2(av[q * 8 + 4], av[q * 8 + 5]), pack_half2(av[q * 8 + 6], av[q * 8 + 7]));
         }
       };
-      float xa[16], xb[16];
-      gather16(xa, 0);
+      gather64(0);
       mbar_wait_guard(bar(C_OP_EMPTY + g), ph ^ 1);
       trace_stamp(2 + g, i, 1, f == 0);
-#pragma unroll 1
-      for (int c16 = 0; c16 < 8; c16 += 2) {
-        gather16(xb, c16 + 1);
-        emit16(xa, c16);
-        if (c16 + 2 < 8) gather16(xa, c16 + 2);
-        emit16(xb, c16 + 1);
-      }
+      emit64(0);
+      gather64(1);
+      emit64(1);
       fence_async_smem();
       mbar_arrive(bar(C_GW_FULL + g));
       mbar_arrive(bar(C_META_EMPTY + ms));
@@ -714,15 +715,16 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         mma_commit(bar(C_ST_EMPTY + s));
         mma_commit(bar(C_D4_FULL + q4));
       };
-      issue1(0);
-      for (int i = 0; i < n_my; ++i) {
-        // order matters: the issuer blocks in program order, so MMA4(i-1) (inputs ready early, releases the
-        // stash for the next tanh phase) must not queue behind MMA3(i), which waits for the gather warps
-        if (i + 1 < n_my) issue1(i + 1);
-        if (i >= 1) issue4(i - 1);
-        issue3(i);
+      // One issuer warp per GEMM: an issuer blocks in program order on its mbarriers, and with a single issuer
+      // MMA3(i) queued behind MMA1(i+1) (which waits for the previous tile's phase B) - 3.8k idle cycles per tile
+      // in the timeline trace.  tcgen05.commit tracks the MMAs of the issuing thread only, which is what we want.
+      if (warp == 16) {
+        for (int i = 0; i < n_my; ++i) issue1(i);
+      } else if (warp == 17) {
+        for (int i = 0; i < n_my; ++i) issue3(i);
+      } else {
+        for (int i = 0; i < n_my; ++i) issue4(i);
       }
-      issue4(n_my - 1);
     }
   }
   __syncthreads();
@@ -783,7 +785,7 @@ extern "C" int fmd_filter_cfconv_bwd2(const float* dist, const int32_t* edge_own
   }
   const int max_tiles = fmd_div_up(capacity, TILE);
   const int grid = max_tiles < fmd_num_sms() ? max_tiles : fmd_num_sms();
-  kern<<<grid, NTHREADS, BSMEM_ALLOC, st>>>(dist, edge_owner, edge_nbr, capacity, n_edges_dev, (const __half*)wf0_h,
+  kern<<<grid, BWD_THREADS, BSMEM_ALLOC, st>>>(dist, edge_owner, edge_nbr, capacity, n_edges_dev, (const __half*)wf0_h,
                                             (const __half*)bf0_h, (const __half*)wf1_h, centers, num_rbf, gamma, rc, a,
                                             g_m, g_d, accumulate);
   FMD_CHECK_LAUNCH();

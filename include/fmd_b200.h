@@ -269,6 +269,11 @@ int fmd_baoab_pre(float* pos, float* vel, const float* forces, const float* inv_
                   const float* noise, uint64_t seed, uint64_t step, const uint64_t* step_dev, int n_nodes,
                   float dt, float vscale, float noisescale, void* stream);
 
+/* Issues prefetch.global.L2 for [ptr, ptr+bytes): warms the 126 MB L2 with a node-feature matrix that a later
+ * edge kernel gathers row-wise (first touches would otherwise pay DRAM latency inside a latency-bound loop).
+ * Part of the fused step only; no reference counterpart. */
+int fmd_l2_prefetch(const void* ptr, uint64_t bytes, void* stream);
+
 /* *counter += 1 on the stream (keeps the Philox step counter on the device so a captured CUDA
  * graph of the whole step can be replayed; fmd_baoab_pre adds *step_dev to `step`). */
 int fmd_increment_u64(uint64_t* counter, void* stream);
