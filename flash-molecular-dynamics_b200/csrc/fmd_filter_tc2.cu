@@ -313,9 +313,10 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
 // =================================================================================================
 // Backward (see fmd_filter_tc.cu for the math), warp-specialised:
 //   PE warps 0-3   thread-per-edge: produce(i) = metadata + rbf row; e4(i-2) = D4 -> g_d
-//   G0 warps 4-7   thread-per-feature, even tiles: row f of gW0^T = a[nbr,f] * g_m[owner,f]; then D1 -> t (stash)
+//   G0 warps 4-7   even tiles: thread-per-feature row f of gW0^T = a[nbr,f] * g_m[owner,f]; then, thread-per-edge,
+//                  D1^T -> t row (stash)
 //   G1 warps 8-11  same for odd tiles
-//   T  warps 12-15 thread-per-feature: D3 -> g_t row (in place over t) + cut-term sums
+//   T  warps 12-15 thread-per-EDGE: D3^T -> g_t row (in place over t) + in-thread cut-off term sum
 //   M  warps 16-18 one MMA-issuer thread each: D13[s] = Wf0.rbf^T | D13[s] = Wf1^T.gW0^T | D4[q] = g_t.Wf0
 constexpr uint32_t BO_WF0 = 0;
 constexpr uint32_t BO_WF1 = BO_WF0 + 128 * 128;
@@ -325,8 +326,8 @@ constexpr uint32_t BO_ST = BO_OP + 2 * 2 * 128 * 128;        // 2 x 32 KB: t^T s
 constexpr uint32_t BO_META = BO_ST + 2 * 2 * 128 * 128;      // 4 x 1 KB
 constexpr uint32_t BO_OWN = BO_META + META_STAGES * TILE * 8;
 constexpr uint32_t BO_HEAD = BO_OWN + META_STAGES * TILE * 4;  // 4 x 16 B boundary masks
-constexpr uint32_t BO_RED = BO_HEAD + META_STAGES * 16;      // 4 x [4][128] floats
-constexpr uint32_t BO_BIAS = BO_RED + 4 * 4 * TILE * 4;
+constexpr uint32_t BO_RED = BO_HEAD + META_STAGES * 16;      // 4 x [128] floats: cut-off term sum per edge
+constexpr uint32_t BO_BIAS = BO_RED + 4 * TILE * 4;
 constexpr uint32_t BO_CEN = BO_BIAS + NF * 4;
 constexpr uint32_t BO_BAR = BO_CEN + RP * 4;
 constexpr uint32_t BSMEM = BO_BAR + 40 * 8 + 16;
@@ -448,8 +449,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         }
       }
       if (kExact) {
-        const float* red = reinterpret_cast<const float*>(smem + BO_RED + s * (4 * TILE * 4));
-        acc += dcut * (red[tid] + red[TILE + tid] + red[2 * TILE + tid] + red[3 * TILE + tid]);
+        acc += dcut * reinterpret_cast<const float*>(smem + BO_RED + s * (TILE * 4))[tid];
       }
       fence_before_sync();
       mbar_arrive(bar(C_D4_EMPTY + s));
@@ -499,9 +499,12 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
     const float* __restrict__ af = a + f;
     const float* __restrict__ gmf = g_m + f;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    const float bias = sBias[f];
     // tanh phase of the same tile (D1 -> t -> stash), done by the gather group: these warps idle ~60 % of a tile
     // period waiting for buffers, while the dedicated T warps are the longest role (timeline trace)
+    // In the backward everything except the gather is computed with a TMEM lane (= thread) per EDGE:
+    // D1^T[e,j], D3^T[e,j], D4[e,k].  Thread e then owns row e of t / g_t (K-major A operand of the last GEMM,
+    // written in place), C(d_e) is a per-thread scalar and the exact cut-off term sum_j t_j D3_j is an in-thread
+    // FMA chain - no cross-lane reduction at all (the feature-per-lane variant spent 1/3 of its time in shuffles).
     auto phaseA = [&](int i) {
       const int s = i & 1;
       const uint32_t ph = (i >> 1) & 1;
@@ -511,6 +514,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_wait_guard(bar(C_ST_EMPTY + s), ph ^ 1);   // MMA4(i-2) has consumed g_t from sT[s]
       trace_stamp(4, i, 1, f == 0);
       fence_after_sync();
+      const float4* sBias4 = reinterpret_cast<const float4*>(sBias);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
@@ -518,12 +522,14 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          const float4 ba = sBias4[c * 8 + q * 2], bb = sBias4[c * 8 + q * 2 + 1];
+          const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           uint32_t p[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            p[u] = pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u]) + bias),
-                              tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]) + bias));
-          const int chunk = c * 4 + q;
+            p[u] = pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u]) + bj[2 * u]),
+                              tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]) + bj[2 * u + 1]));
+          const int chunk = c * 4 + q;   // 8 consecutive features j of edge row f (= this thread's edge)
           *reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(f, chunk & 7)) =
               make_uint4(p[0], p[1], p[2], p[3]);
         }
@@ -593,64 +599,50 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
   } else if (warp < 16) {
     // =========================================================== T (thread = feature j)
     const int j = (warp & 3) * 32 + lane;
-    const int wq = warp & 3;
-    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
-    const float bias = sBias[j];
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     auto phaseB = [&](int i) {
       const int s = i & 1, ms = i & (META_STAGES - 1);
       const uint32_t ph = (i >> 1) & 1;
-      // g_t overwrites t IN PLACE in the stash (same thread, same address), so the gW0 buffer sOp[s] is free as
-      // soon as MMA3 has read it and the gather warps never wait for MMA4
+      // thread j here is EDGE row j of the tile.  g_t overwrites t IN PLACE (same thread, same address) and the
+      // buffer then is the K-major A operand of MMA4; the gW0 buffer sOp[s] is free as soon as MMA3 has read it.
       uint8_t* sT = smem + BO_ST + s * (2 * 128 * 128);
-      const uint4* sMeta2 = reinterpret_cast<const uint4*>(smem + BO_META + ms * TILE * 8);
       const int q4 = i & (D4_STAGES - 1);
-      float* red = reinterpret_cast<float*>(smem + BO_RED + q4 * (4 * TILE * 4));
+      float* red = reinterpret_cast<float*>(smem + BO_RED + q4 * (TILE * 4));
       trace_stamp(5, i, 0, j == 0);
       mbar_wait_guard(bar(C_ST_FULL + s), ph);     // t of this tile written by the gather/tanh group
       mbar_wait_guard(bar(C_D3_FULL + s), ph);
       if (kExact) mbar_wait_guard(bar(C_D4_EMPTY + q4), ((i / D4_STAGES) & 1) ^ 1);  // e4(i-4) has read sRed[q4]
       trace_stamp(5, i, 1, j == 0);
       fence_after_sync();
+      const float cut = __uint_as_float(reinterpret_cast<const uint2*>(smem + BO_META + ms * TILE * 8)[j].y);
+      float usum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem + s * 128 + lane_sel + c * 32, r);
         tmem_ld_wait();
-        float uu[32];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = c * 4 + q;
-          const uint4 tq = *reinterpret_cast<const uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7));
+          uint4* slot = reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7));
+          const uint4 tq = *slot;
           const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
           uint32_t p[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int k = q * 8 + 2 * u;
             const float2 tt = unpack_h2(tw[u]);
-            const uint4 m = sMeta2[c * 16 + q * 4 + u];  // cuts of edges k, k+1
             const float d0 = __uint_as_float(r[k]), d1 = __uint_as_float(r[k + 1]);
-            uu[k] = tt.x * d0;
-            uu[k + 1] = tt.y * d1;
-            p[u] = pack_half2(__uint_as_float(m.y) * d0 * fmaf(-tt.x, tt.x, 1.f),
-                              __uint_as_float(m.w) * d1 * fmaf(-tt.y, tt.y, 1.f));
-          }
-          *reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7)) =
-              make_uint4(p[0], p[1], p[2], p[3]);
-        }
-        if (kExact) {
-#pragma unroll
-          for (int w = 16; w >= 1; w >>= 1) {
-            const bool up = (lane & w) != 0;
-#pragma unroll
-            for (int u = 0; u < w; ++u) {
-              const float send = up ? uu[u] : uu[u + w];
-              const float keep = up ? uu[u + w] : uu[u];
-              uu[u] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            if (kExact) {
+              usum = fmaf(tt.x, d0, usum);
+              usum = fmaf(tt.y, d1, usum);
             }
+            p[u] = pack_half2(cut * d0 * fmaf(-tt.x, tt.x, 1.f), cut * d1 * fmaf(-tt.y, tt.y, 1.f));
           }
-          red[wq * TILE + c * 32 + lane] = uu[0];
+          *slot = make_uint4(p[0], p[1], p[2], p[3]);
         }
       }
+      if (kExact) red[j] = usum;
       fence_before_sync();
       mbar_arrive(bar(C_D3_EMPTY + s));
       fence_async_smem();
@@ -662,12 +654,12 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
   } else {
     // =========================================================== M: MMA issuer
     if (lane == 0 && n_my > 0) {
-      constexpr uint32_t IDESC1 = idesc_f16(128, 128, 0, 0);
-      constexpr uint32_t IDESC3 = idesc_f16(128, 128, 1, 1);
-      constexpr uint32_t IDESC4 = idesc_f16(128, 64, 1, 1);
-      const uint64_t dA1 = smem_desc_sw128(sbase + BO_WF0, 16, 1024);
-      const uint64_t dA3 = smem_desc_sw128(sbase + BO_WF1, 128 * 128, 1024);  // Wf1 [f][j] read MN-major (M = j)
-      const uint64_t dB4 = smem_desc_sw128(sbase + BO_WF0, 16, 1024);         // Wf0 [j][k] read MN-major (N = k)
+      constexpr uint32_t IDESC1 = idesc_f16(128, 128, 0, 0);   // D1^T[e,j]: A = rbf tile (K-major), B = Wf0 (K-major)
+      constexpr uint32_t IDESC3 = idesc_f16(128, 128, 1, 1);   // D3^T[e,j]: A = gW0^T [f][e] (MN-major), B = Wf1 [f][j] (MN-major)
+      constexpr uint32_t IDESC4 = idesc_f16(128, 64, 0, 1);    // D4[e,k]:   A = g_t [e][j] (K-major),   B = Wf0 [j][k] (MN-major)
+      const uint64_t dW0k = smem_desc_sw128(sbase + BO_WF0, 16, 1024);          // Wf0 as K-major operand (rows j)
+      const uint64_t dW1mn = smem_desc_sw128(sbase + BO_WF1, 128 * 128, 1024);  // Wf1 [f][j] read MN-major (N = j)
+      const uint64_t dB4 = smem_desc_sw128(sbase + BO_WF0, 16, 1024);           // Wf0 [j][k] read MN-major (N = k)
       auto issue1 = [&](int i) {
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
@@ -678,7 +670,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         fence_after_sync();
         const uint64_t dB1 = smem_desc_sw128(sbase + BO_RBF + s * (128 * 128), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < RP / 16; ++k) mma_f16(tmem + s * 128, dA1 + 2 * k, dB1 + 2 * k, IDESC1, k > 0);
+        for (int k = 0; k < RP / 16; ++k) mma_f16(tmem + s * 128, dB1 + 2 * k, dW0k + 2 * k, IDESC1, k > 0);
         mma_commit(bar(C_RBF_EMPTY + s));
         mma_commit(bar(C_D1_FULL + s));
       };
@@ -694,7 +686,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         const uint64_t dB3 = smem_desc_sw128(sbase + BO_OP + s * (2 * 128 * 128), 128 * 128, 1024);
 #pragma unroll
         for (int k = 0; k < NF / 16; ++k)
-          mma_f16(tmem + s * 128, dA3 + (uint64_t)(k * (2048 / 16)), dB3 + (uint64_t)(k * (2048 / 16)), IDESC3, k > 0);
+          mma_f16(tmem + s * 128, dB3 + (uint64_t)(k * (2048 / 16)), dW1mn + (uint64_t)(k * (2048 / 16)), IDESC3, k > 0);
         mma_commit(bar(C_OP_EMPTY + s));
         mma_commit(bar(C_D3_FULL + s));
       };
@@ -707,11 +699,11 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         mbar_wait_guard(bar(C_D4_EMPTY + q4), ((i / D4_STAGES) & 1) ^ 1);
         trace_stamp(8, i, 1, true);
         fence_after_sync();
-        const uint64_t dA4 = smem_desc_sw128(sbase + BO_ST + s * (2 * 128 * 128), 128 * 128, 1024);
+        const uint64_t dA4 = smem_desc_sw128(sbase + BO_ST + s * (2 * 128 * 128), 16, 1024);   // g_t [e][j], K-major
 #pragma unroll
         for (int k = 0; k < NF / 16; ++k)
-          mma_f16(tmem + 256 + q4 * 64, dA4 + (uint64_t)(k * (2048 / 16)), dB4 + (uint64_t)(k * (2048 / 16)), IDESC4,
-                  k > 0);
+          mma_f16(tmem + 256 + q4 * 64, dA4 + (uint64_t)((k >> 2) * (128 * 128 / 16) + (k & 3) * 2),
+                  dB4 + (uint64_t)(k * (2048 / 16)), IDESC4, k > 0);
         mma_commit(bar(C_ST_EMPTY + s));
         mma_commit(bar(C_D4_FULL + q4));
       };

@@ -373,11 +373,6 @@ class ForceField:
         self._n += 1
         for l in range(nb - 1, -1, -1):
             # h_{l+1} = h_l + c Wl^T + bl ; c = tanh(m W2^T + b2)
-            if tc:
-                # a[l] was last touched in the forward pass and has left L2: warm it while the node GEMMs run, the
-                # backward edge kernel gathers its rows in a latency-bound pattern
-                L.call("fmd_l2_prefetch", L.ptr(self.a[l]), self.a[l].numel() * 4, st)
-                self._n += 1
             self._lin(gh_cur, k[f"b{l}.lin_w"], None, self.g_c, aux=self.c[l])
             self._lin(self.g_c, k[f"b{l}.lin2_w"], None, self.g_m)
             if tc:
