@@ -361,6 +361,43 @@ def test_fused_tensor_core_path_vs_materialised_path(exact):
     assert torch.equal(f1, f3) and torch.equal(e1, e3)
 
 
+def test_fused_tensor_core_path_ragged_molecules_and_isolated_beads():
+    """Ragged batch (molecules of 1..300 beads, beads without any neighbour, segments longer than a 128-edge
+    tile, an edge count that is not a multiple of the tile): fused tcgen05 path vs the oracle's W16A16 model
+    and vs the materialised path; edge capacity with slack (unused tail tiles)."""
+    from flashmd.engine import ForceField, SchNetWeights, random_schnet_tensors
+    sizes = [1, 2, 33, 7, 130, 64, 300, 1, 5, 180]
+    pos_np, ptr_np = _random_molecules(11, sizes, box=16.0)
+    pos_np[ptr_np[-2]:] *= 5.0 / 16.0            # last molecule: 180 beads in a 5 A box -> degrees > 128
+    rc = 6.0
+    pos = torch.from_numpy(pos_np).to(DEV).contiguous()
+    ptr = torch.from_numpy(ptr_np).to(DEV)
+    N = pos.shape[0]
+    types = (torch.arange(N) % 7 + 1).to(DEV)
+    tensors = random_schnet_tensors(9, embedding_size=10)
+    w = SchNetWeights.from_flat(tensors, rc, 50, DEV)
+    ff_tc = ForceField(w, [], types, ptr, precision="w16a16", edge_capacity=60000)
+    ff_mat = ForceField(w, [], types, ptr, precision="w16a16", use_tensor_cores=False)
+    e1, f1 = [t.clone() for t in ff_tc.compute(pos)]
+    e2, f2 = [t.clone() for t in ff_mat.compute(pos)]
+    E = ff_tc.num_edges()
+    deg = (ff_tc.seg_ptr[1:] - ff_tc.seg_ptr[:-1])
+    assert int((deg == 0).sum()) > 0 and int(deg.max()) > 128 and E % 128 != 0 and E < 60000
+    assert torch.isfinite(f1).all()
+    assert rel_l2(f1.cpu(), f2.cpu()) < 3e-3 and rel_l2(e1.cpu(), e2.cpu()) < 3e-3
+    tt = {k: v for k, v in tensors.items()}
+    tt.setdefault("out2_b", None)
+    P = O.SchNetParams(tt, 3, 3, rc, 50)
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    ei = torch.stack([ff_tc.src[:E], ff_tc.dst[:E]]).cpu().long()
+    assert np.array_equal(ei.numpy(), O.radius_graph(pos_np, ptr_np, rc))
+    e_ref, f_ref = O.schnet_energy_forces(P, torch.from_numpy(pos_np), types.cpu(), batch, len(sizes), ei,
+                                          precision="w16a16")
+    assert rel_l2(f1.cpu(), f_ref) < 1e-2 and rel_l2(e1.cpu(), e_ref) < 1e-2
+    # beads without neighbours feel no SchNet force
+    assert float(f1[deg == 0].abs().max()) == 0.0
+
+
 def test_edge_capacity_and_large_batch_properties():
     """cfg2-shaped (B=128, n=269) run: size-independent properties — edge list symmetric and sorted,
     forces sum to zero per molecule (translation invariance), identical molecules give identical
