@@ -49,6 +49,7 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
   // ---- two-body terms: entry = {other | kind << 28, p0, p1, p2}
   if (pair_ptr) {
     const int p1 = __ldg(&pair_ptr[a + 1]);
+#pragma unroll 4   // independent record -> position load chains in flight (the loop is latency-bound)
     for (int p = __ldg(&pair_ptr[a]) + lane; p < p1; p += 32) {
       const int4 ent = __ldg(&pair_ent[p]);
       const int other = ent.x & 0x0FFFFFFF, kind = ent.x >> 28;
