@@ -309,6 +309,42 @@ extern "C" int fmd_prior_energy_forces(int kind, const float* pos, const int32_t
   return FMD_OK;
 }
 
+// Last output layer (hidden -> 1, no bias) and the first step of its backward in one pass over y:
+//   e_atom[i] = sum_k y[i,k] w[k] ;  g_y[i,k] = w[k] (1 - y[i,k]^2)      (dE/d e_atom = 1)
+// One warp per node; replaces a [N,K]x[K,1] and a [N,1]x[1,K] launch of the generic dense kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+out_head_kernel(const T* __restrict__ y, const T* __restrict__ w, int n_nodes, int K, float* __restrict__ e_atom,
+                T* __restrict__ g_y) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_nodes) return;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float yv = to_f32<T>(y[(size_t)i * K + k]), wv = to_f32<T>(w[k]);
+    acc = fmaf(yv, wv, acc);
+    if (g_y) g_y[(size_t)i * K + k] = from_f32<T>(wv * (1.0f - yv * yv));
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) e_atom[i] = acc;
+}
+
+extern "C" int fmd_out_head(const void* y, const void* w, int dt, int n_nodes, int n_hidden, float* e_atom, void* g_y,
+                            void* stream) {
+  FMD_REQUIRE(y && w && e_atom && n_hidden > 0, "fmd_out_head: bad arguments");
+  FMD_REQUIRE(dt == FMD_F32 || dt == FMD_F16, "fmd_out_head: bad dtype");
+  if (n_nodes <= 0) return FMD_OK;
+  const int grid = fmd_div_up((long long)n_nodes * 32, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == FMD_F32)
+    out_head_kernel<float><<<grid, 256, 0, st>>>((const float*)y, (const float*)w, n_nodes, n_hidden, e_atom, (float*)g_y);
+  else
+    out_head_kernel<__half><<<grid, 256, 0, st>>>((const __half*)y, (const __half*)w, n_nodes, n_hidden, e_atom,
+                                                   (__half*)g_y);
+  FMD_CHECK_LAUNCH();
+  return FMD_OK;
+}
+
 // L2 warm-up of a buffer that a later gather kernel will read in a latency-bound pattern
 __global__ void __launch_bounds__(256) l2_prefetch_kernel(const char* __restrict__ p, size_t bytes) {
   const size_t line = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128;

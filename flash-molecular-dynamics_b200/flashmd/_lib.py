@@ -60,6 +60,7 @@ _SIGS = {
     "fmd_linear_tc": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                        c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
     "fmd_embedding": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
+    "fmd_out_head": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "fmd_segment_sum": ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
     "fmd_prior_energy_forces": ([c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p], c_int),

@@ -351,19 +351,25 @@ class ForceField:
         # output network
         no = w.num_out_layers
         x = self.h[nb]
-        for i in range(no):
+        # the last layer (hidden -> 1, no bias) and the first backward step are one pass over the last hidden layer
+        head = no >= 2 and k.get(f"out{no - 1}_b{sfx}") is None and self.y[-1].shape[1] == 1
+        for i in range(no - 1 if head else no):
             last = i == no - 1
             b = k.get(f"out{i}_b{sfx}")
             self._lin(x, k[f"out{i}_wT{sfx}"], b, self.y[i], x_round=(w16 and x.dtype == torch.float32),
                       epi_act=(L.ACT_NONE if last else tanh_f))
             x = self.y[i]
+        if head:
+            L.call("fmd_out_head", L.ptr(x), L.ptr(k[f"out{no - 1}_w{sfx}"]), L.dt_code(x), self.N, x.shape[1],
+                   L.ptr(self.y[-1]), L.ptr(self.g_y[no - 2]), st)
+            self._n += 1
         assert self.y[-1].shape[1] == 1
         L.call("fmd_segment_sum", L.ptr(self.y[-1]), L.ptr(self.mol_ptr), self.B, L.ptr(self.energy), 0, st)
         self._n += 1
         # ---------------- backward
         # dE/d(e_atom) = 1  ->  through the output MLP
-        g = self.ones
-        for i in range(no - 1, 0, -1):
+        g = self.g_y[no - 2] if head else self.ones
+        for i in range(no - 2 if head else no - 1, 0, -1):
             # g_y[i-1] = (g @ out_i_w[out,in]) * (1 - y[i-1]^2)
             self._lin(g, k[f"out{i}_w{sfx}"], None, self.g_y[i - 1], aux=self.y[i - 1], x_round=(w16 and g.dtype == torch.float32))
             g = self.g_y[i - 1]

@@ -221,6 +221,12 @@ int fmd_linear_tc(const void* X, int xdt, const void* W, int wdt, const void* bi
 int fmd_embedding(const float* table, const void* types, int idx_bytes, int n_nodes, int n_feat, float* out,
                   void* stream);
 
+/* replaces: the last layer of the output MLP (Linear(hidden, 1, bias=False), models/schnet.py:829-834 /
+ * models/gptq.py:304) and the first step of its backward, in one pass over y [n_nodes, n_hidden] (dt = FMD_F32 |
+ * FMD_F16, also the type of w [n_hidden] and g_y):  e_atom[i] = sum_k y[i,k] w[k] ;  g_y[i,k] = w[k] (1 - y[i,k]^2)
+ * (the gradient of sum(e_atom) w.r.t. the pre-activation of the last hidden layer; g_y nullable). */
+int fmd_out_head(const void* y, const void* w, int dt, int n_nodes, int n_hidden, float* e_atom, void* g_y, void* stream);
+
 /* replaces: scatter(energy, batch, reduce="sum") (models/schnet.py:355-357) for sorted `batch`:
  * out[b] (+)= sum_{i in [mol_ptr[b], mol_ptr[b+1])} e_atom[i]; deterministic block reduction. */
 int fmd_segment_sum(const float* e_atom, const int32_t* mol_ptr, int n_mols, float* out, int accumulate,
