@@ -225,6 +225,201 @@ linear_tc_kernel(const TX* __restrict__ X, const TW* __restrict__ W, const TW* _
   if (warp_all == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Chain of up to FMD_MAX_CHAIN dense layers on the same rows: the output tile of stage s (after its epilogue) is
+// written back into the A-operand buffer IN PLACE and feeds stage s+1 without leaving the SM; the stage weights
+// are streamed through the one shared weight buffer (they are L2-resident).  Same two-group structure.
+struct ChainArgs {
+  fmd_dense_stage st[FMD_MAX_CHAIN];
+  int n_stages;
+};
+
+__device__ __forceinline__ float4 load4_dt(const void* p, size_t idx, int dt) {
+  return dt == FMD_F16 ? load4(reinterpret_cast<const __half*>(p) + idx) : load4(reinterpret_cast<const float*>(p) + idx);
+}
+__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+
+__global__ void __launch_bounds__(LT_THREADS, 1)
+linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int pro_act, int x_round_f16,
+                       const __grid_constant__ ChainArgs ca) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const uint32_t sbase = smem_u32(smem);
+  const int tid_all = threadIdx.x, warp_all = tid_all >> 5;
+  const int group = tid_all >> 7;
+  const int tid = tid_all & (LT_TILE - 1);
+  const int warp = tid >> 5;
+  float* sBias = reinterpret_cast<float*>(smem + LO_BIAS);
+  const uint32_t bar = sbase + LO_BAR + 8u * group;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + LO_BAR + 16);
+  uint8_t* sA = smem + LO_A + group * (64 * 1024);
+  const int n_tiles = (M + LT_TILE - 1) / LT_TILE;
+  if (tid_all == 0) {
+    mbar_init(sbase + LO_BAR, 1);
+    mbar_init(sbase + LO_BAR + 8, 1);
+    fence_mbar_init();
+  }
+  if (warp_all == 0) {
+    __syncwarp();
+    tmem_alloc(sbase + LO_BAR + 16, 256);
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem = tmem_base + group * 128;
+  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint64_t dA = smem_desc_sw128(sbase + LO_A + group * (64 * 1024), 16, 1024);
+  const uint64_t dB = smem_desc_sw128(sbase + LO_B, 16, 1024);
+  uint32_t it = 0;
+  for (int tile0 = blockIdx.x * LT_GROUPS; tile0 < n_tiles; tile0 += gridDim.x * LT_GROUPS) {
+    const int m0 = (tile0 + group) * LT_TILE;   // may lie beyond M for the second group: rows are then all invalid
+    // ---- stage pro(X) tile
+    {
+      const int kc = K0 >> 2, kc_shift = (K0 == 128) ? 5 : 4;
+      const int total = LT_TILE << kc_shift;
+      for (int base = 0; base < total; base += LT_TILE * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = base + u * LT_TILE + tid;
+          const int r = idx >> kc_shift, c = idx & (kc - 1);
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0 + r < M) v[u] = load4_dt(X, (size_t)(m0 + r) * K0 + c * 4, xdt);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = base + u * LT_TILE + tid;
+          const int r = idx >> kc_shift, c = idx & (kc - 1);
+          float4 t = v[u];
+          if (x_round_f16) { t.x = round_h(t.x); t.y = round_h(t.y); t.z = round_h(t.z); t.w = round_h(t.w); }
+          if (pro_act) { t.x = act(t.x, pro_act); t.y = act(t.y, pro_act); t.z = act(t.z, pro_act); t.w = act(t.w, pro_act); }
+          t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
+          *reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(r, c & 7)) = t;
+        }
+      }
+    }
+    int K = K0;
+    for (int s = 0; s < ca.n_stages; ++s) {
+      const fmd_dense_stage& S = ca.st[s];
+      const int N = S.N;
+      fence_before_sync();
+      __syncthreads();   // both groups are done with the previous stage's weights (their MMAs completed)
+      // ---- stage-s weights [N][K] -> K-major B operand, all 256 threads, 8 chunks in flight
+      {
+        const int kc = K >> 2, kc_shift = (K == 128) ? 5 : 4;
+        const int total = N << kc_shift;
+        for (int base = 0; base < total; base += LT_THREADS * 8) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * LT_THREADS + tid_all;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < total) v[u] = load4_dt(S.W, (size_t)idx * 4, S.wdt);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * LT_THREADS + tid_all;
+            const int n = idx >> kc_shift, c = idx & (kc - 1);
+            float4 t = v[u];
+            t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
+            if (idx < total) *reinterpret_cast<float4*>(smem + LO_B + (c >> 3) * (N * 128) + sw128_off(n, c & 7)) = t;
+          }
+        }
+        if (tid_all < N)
+          sBias[tid_all] = S.bias ? (S.wdt == FMD_F16 ? __half2float(reinterpret_cast<const __half*>(S.bias)[tid_all])
+                                                       : reinterpret_cast<const float*>(S.bias)[tid_all])
+                                  : 0.f;
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        const uint32_t idesc = idesc_tf32(128, N, 0, 0);
+        const uint32_t b_kblock = (uint32_t)(N * 128 / 16);
+        for (int k = 0; k < K / 8; ++k)
+          mma_tf32(tmem, dA + (uint64_t)((k >> 2) * (128 * 128 / 16) + (k & 3) * 2),
+                   dB + (uint64_t)((k >> 2) * b_kblock + (k & 3) * 2), idesc, k > 0);
+        mma_commit(bar);
+      }
+      mbar_wait(bar, it & 1u);
+      ++it;
+      fence_after_sync();
+      // ---- epilogue of stage s, two phases:
+      //  1. thread r drains accumulator row r: + bias, activation -> row r of the A-operand buffer, in place (the MMA
+      //     that read the buffer has completed);
+      //  2. the group walks the tile in row-major order, consecutive threads on consecutive 16-byte chunks of a row, so
+      //     the aux / residual loads and the output stores are fully coalesced (row-per-thread global access made
+      //     this epilogue 5x slower than the GEMM itself); the tile is rewritten as the TF32 operand of the next stage.
+      const bool feed = s + 1 < ca.n_stages;
+      const bool post = S.aux || S.res || S.Y;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(tmem + lane_sel + c0, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(rr[q * 4 + u]) + sBias[c0 + q * 4 + u];
+          if (S.epi_act) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = act(v[u], S.epi_act);
+          }
+          if (!post) {   // nothing else to apply: write the final operand form directly
+            if (S.round_f16) { v[0] = round_h(v[0]); v[1] = round_h(v[1]); v[2] = round_h(v[2]); v[3] = round_h(v[3]); }
+            v[0] = to_tf32(v[0]); v[1] = to_tf32(v[1]); v[2] = to_tf32(v[2]); v[3] = to_tf32(v[3]);
+          }
+          const int c = (c0 >> 2) + q;
+          *reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(tid, c & 7)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+      if (post) {
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(LT_TILE) : "memory");
+        const int nc = N >> 2, nc_shift = (N == 128) ? 5 : 4;
+        const int total = LT_TILE << nc_shift;
+        for (int base = 0; base < total; base += LT_TILE * 8) {
+          float4 av[8], rv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * LT_TILE + tid;
+            const int r = idx >> nc_shift, c = idx & (nc - 1);
+            const size_t o = (size_t)(m0 + r) * N + c * 4;
+            const bool ok = m0 + r < M;
+            av[u] = (S.aux && ok) ? load4_dt(S.aux, o, S.auxdt) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rv[u] = (S.res && ok) ? load4(S.res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * LT_TILE + tid;
+            const int r = idx >> nc_shift, c = idx & (nc - 1);
+            float4* slot = reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(r, c & 7));
+            float4 v = *slot;
+            v.x = fmaf(v.x, -av[u].x * av[u].x, v.x) + rv[u].x;     // v * (1 - aux^2) + res
+            v.y = fmaf(v.y, -av[u].y * av[u].y, v.y) + rv[u].y;
+            v.z = fmaf(v.z, -av[u].z * av[u].z, v.z) + rv[u].z;
+            v.w = fmaf(v.w, -av[u].w * av[u].w, v.w) + rv[u].w;
+            if (S.Y && m0 + r < M) {
+              const size_t o = (size_t)(m0 + r) * N + c * 4;
+              if (S.ydt == FMD_F16) store4(reinterpret_cast<__half*>(S.Y) + o, v);
+              else store4(reinterpret_cast<float*>(S.Y) + o, v);
+            }
+            if (feed) {
+              if (S.round_f16) { v.x = round_h(v.x); v.y = round_h(v.y); v.z = round_h(v.z); v.w = round_h(v.w); }
+              *slot = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            }
+          }
+        }
+      }
+      K = N;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp_all == 0) tmem_dealloc(tmem_base, 256);
+}
+
 template <typename TX, typename TW, typename TY>
 int launch_tc(const void* X, const void* W, const void* bias, void* Y, int M, int N, int K, const int32_t* m_dev,
               int pro_act, int x_round, int epi_act, const void* aux, int auxdt, const float* res, int w_nk, cudaStream_t st) {
@@ -269,6 +464,30 @@ extern "C" int fmd_linear_tc(const void* X, int xdt, const void* W, int wdt, con
   }
 #undef FMD_LT
   if (rc != FMD_OK) return rc;
+  FMD_CHECK_LAUNCH();
+  return FMD_OK;
+}
+
+extern "C" int fmd_linear_chain_tc(const void* X, int xdt, int M, int K, int pro_act, int x_round_f16,
+                                   const fmd_dense_stage* stages, int n_stages, void* stream) {
+  FMD_REQUIRE(X && stages && M >= 0 && n_stages >= 1 && n_stages <= FMD_MAX_CHAIN, "fmd_linear_chain_tc: bad arguments");
+  FMD_REQUIRE(K == 64 || K == 128, "fmd_linear_chain_tc: K must be 64 or 128");
+  ChainArgs ca;
+  ca.n_stages = n_stages;
+  for (int s = 0; s < n_stages; ++s) {
+    ca.st[s] = stages[s];
+    FMD_REQUIRE(stages[s].W && (stages[s].N == 64 || stages[s].N == 128), "fmd_linear_chain_tc: stage needs W and N in {64,128}");
+    FMD_REQUIRE(stages[s].Y || s + 1 < n_stages, "fmd_linear_chain_tc: the last stage must store its output");
+  }
+  if (M == 0) return FMD_OK;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FMD_CUDA(cudaFuncSetAttribute(linear_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM_ALLOC));
+    attr_done = true;
+  }
+  const int pairs = fmd_div_up(fmd_div_up(M, LT_TILE), LT_GROUPS);
+  const int grid = pairs < fmd_num_sms() ? pairs : fmd_num_sms();
+  linear_chain_tc_kernel<<<grid, LT_THREADS, LT_SMEM_ALLOC, (cudaStream_t)stream>>>(X, xdt, M, K, pro_act, x_round_f16, ca);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

@@ -21,6 +21,16 @@ PRIOR_BONDS, PRIOR_ANGLES, PRIOR_DIHEDRALS, PRIOR_REPULSION = 0, 1, 2, 3
 
 _lib = None
 
+
+class DenseStage(ctypes.Structure):
+    """fmd_dense_stage of include/fmd_b200.h."""
+    _fields_ = [("W", c_void_p), ("bias", c_void_p), ("wdt", c_int), ("N", c_int), ("epi_act", c_int),
+                ("aux", c_void_p), ("auxdt", c_int), ("res", c_void_p), ("Y", c_void_p), ("ydt", c_int),
+                ("round_f16", c_int)]
+
+
+MAX_CHAIN = 4
+
 _SIGS = {
     "fmd_version": ([], c_int),
     "fmd_sm_count": ([], c_int),
@@ -59,6 +69,8 @@ _SIGS = {
                     c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "fmd_linear_tc": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                        c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
+    "fmd_linear_chain_tc": ([c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(DenseStage), c_int, c_void_p],
+                            c_int),
     "fmd_embedding": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),
     "fmd_out_head": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "fmd_segment_sum": ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),

@@ -277,6 +277,22 @@ class ForceField:
             L.call("fmd_linear", *args, self._st)
         self._n += 1
 
+    def _chain(self, x, stages, pro_act=0, x_round=False):
+        """Consecutive node-level layers in ONE launch (fmd_linear_chain_tc).  stages: dicts with W ([N,K] tensor),
+        bias, epi, aux, res, Y (tensor or None), round (feed the next stage with the fp16-rounded value)."""
+        arr = (L.DenseStage * len(stages))()
+        for s_, d in zip(arr, stages):
+            W = d["W"]
+            s_.W, s_.bias, s_.wdt, s_.N = L.ptr(W), L.ptr(d.get("bias")), L.dt_code(W), W.shape[0]
+            s_.epi_act = d.get("epi", 0)
+            aux, res, Y = d.get("aux"), d.get("res"), d.get("Y")
+            s_.aux, s_.auxdt = L.ptr(aux), (L.dt_code(aux) if aux is not None else 0)
+            s_.res, s_.Y, s_.ydt = L.ptr(res), L.ptr(Y), (L.dt_code(Y) if Y is not None else 0)
+            s_.round_f16 = int(bool(d.get("round", False)))
+        L.call("fmd_linear_chain_tc", L.ptr(x), L.dt_code(x), x.shape[0], x.shape[1], pro_act, int(x_round), arr,
+               len(stages), self._st)
+        self._n += 1
+
     def _cfconv(self, x, W, out):
         L.call("fmd_cfconv_csr", L.ptr(x), L.ptr(W), L.dt_code(W), L.ptr(self.dist), L.ptr(self.dst),
                L.ptr(self.seg_ptr), None, 4, self.N, self.cap, x.shape[1], self.w.cutoff, L.ptr(out), self._st)
@@ -317,7 +333,65 @@ class ForceField:
         return int(self.n_edges_dev.item())
 
     # -- SchNet ----------------------------------------------------------------------------------
+    def _chain_ok(self):
+        w, k = self.w, self.w.k
+        no = w.num_out_layers
+        widths = [w.tensors[f"out{i}_w"].shape[0] for i in range(no)]
+        return (self.fused_tc and w.hidden == 128 and w.filters == 128 and no >= 2 and widths[-1] == 1
+                and all(x in (64, 128) for x in widths[:-1]) and k.get(f"out{no - 1}_b.h") is None
+                and 2 + (no - 1) <= L.MAX_CHAIN)
+
+    def _schnet_tc(self, pos):
+        """W16A16 step with the default widths: 5 fused edge launches + 3 backward edge launches, the node layers
+        as 6 chained tensor-core launches (fmd_linear_chain_tc), nothing else but neighbour list / head / forces."""
+        w, k, st = self.w, self.w.k, self._st
+        nb, no = w.num_blocks, w.num_out_layers
+        T, TC = L.ACT_TANH, L.ACT_TANH_CLAMPED
+        self.build_neighbor_list(pos)
+        L.call("fmd_embedding", L.ptr(k["embedding"]), L.ptr(self.types), 4, self.N, w.hidden, L.ptr(self.h[0]), st)
+        L.call("fmd_embedding", L.ptr(k["emb_lin1"]), L.ptr(self.types), 4, self.N, w.filters, L.ptr(self.a[0]), st)
+        self._n += 2
+        for l in range(nb):
+            self._filter_cfconv(l, self.a[l], self.m)
+            last = l == nb - 1
+            stages = [dict(W=k[f"b{l}.lin2_w"], bias=k[f"b{l}.lin2_b"], epi=T, Y=self.c[l]),
+                      dict(W=k[f"b{l}.lin_w"], bias=k[f"b{l}.lin_b"], res=self.h[l], Y=self.h[l + 1], round=last)]
+            if not last:
+                stages.append(dict(W=k[f"b{l + 1}.lin1_w"], Y=self.a[l + 1]))
+            else:   # output network except its last layer (fp16 operands, clamped tanh, fp16 storage)
+                for i in range(no - 1):
+                    stages.append(dict(W=k[f"out{i}_w.h"], bias=k.get(f"out{i}_b.h"), epi=TC, Y=self.y[i], round=True))
+            self._chain(self.m, stages)
+        L.call("fmd_out_head", L.ptr(self.y[no - 2]), L.ptr(k[f"out{no - 1}_w.h"]), L.F16, self.N, self.y[no - 2].shape[1],
+               L.ptr(self.y[-1]), L.ptr(self.g_y[no - 2]), st)
+        L.call("fmd_segment_sum", L.ptr(self.y[-1]), L.ptr(self.mol_ptr), self.B, L.ptr(self.energy), 0, st)
+        self._n += 2
+        # ---------------- backward.  [N,K] layout of a backward GEMM's weight == the forward weight's transpose.
+        self.g_d.zero_()
+        self._n += 1
+        gh_cur, gh_nxt = self.g_h[0], self.g_h[1]
+        stages = []
+        for i in range(no - 2, 0, -1):      # g_y[i-1] = (g_y[i] @ out_i_w) * (1 - y[i-1]^2), stored as fp16 in the reference
+            stages.append(dict(W=k[f"out{i}_wT.h"], aux=self.y[i - 1], round=True))
+        stages.append(dict(W=k["out0_wT.h"], Y=gh_cur))
+        x = self.g_y[no - 2]
+        for l in range(nb - 1, -1, -1):
+            stages.append(dict(W=k[f"b{l}.lin_wT"], aux=self.c[l]))          # g_c = (g_h @ Wl) * (1 - c^2)
+            stages.append(dict(W=k[f"b{l}.lin2_wT"], Y=self.g_m))           # g_m = g_c @ W2
+            self._chain(x, stages)
+            self._filter_cfconv_bwd(l, self.a[l], self.g_m)
+            if l > 0:   # dE/dh_0 does not enter the forces: no grad_x / g_h update below block 0
+                self._filter_cfconv(l, self.g_m, self.g_a)
+                stages = [dict(W=k[f"b{l}.lin1_wT"], res=gh_cur, Y=gh_nxt)]  # g_h <- g_h + g_a @ W1
+                gh_cur, gh_nxt = gh_nxt, gh_cur
+                x = self.g_a
+        L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(self.seg_ptr), L.ptr(self.dst), L.ptr(self.rev),
+               L.ptr(self.dist), L.ptr(self.g_d), self.N, self.cap, 1.0, L.ptr(self.forces), 0, st)
+        self._n += 1
+
     def _schnet(self, pos):
+        if self._chain_ok():
+            return self._schnet_tc(pos)
         w, k, st = self.w, self.w.k, self._st
         w16 = self.precision == "w16a16"
         nb, ned = w.num_blocks, self.n_edges_dev

@@ -215,6 +215,29 @@ int fmd_linear_tc(const void* X, int xdt, const void* W, int wdt, const void* bi
                   int K, const int32_t* m_dev, int pro_act, int x_round_f16, int epi_act, const void* aux, int auxdt,
                   const float* res, int w_is_nk, void* stream);
 
+/* One dense layer of fmd_linear_chain_tc. W is [N,K] (the nn.Linear.weight layout), K = N of the previous stage. */
+#define FMD_MAX_CHAIN 4
+typedef struct {
+  const void* W;     /* [N,K], wdt */
+  const void* bias;  /* [N] wdt, or NULL */
+  int wdt;           /* FMD_F32 | FMD_F16 */
+  int N;             /* 64 | 128 */
+  int epi_act;       /* FMD_ACT_* applied to X W^T + bias */
+  const void* aux;   /* [M,N] auxdt or NULL: result *= (1 - aux^2)  (tanh-backward fusion) */
+  int auxdt;
+  const float* res;  /* [M,N] f32 or NULL: result += res */
+  void* Y;           /* [M,N] ydt or NULL: store this stage's result (the last stage must store) */
+  int ydt;
+  int round_f16;     /* round the result to fp16 before it feeds the next stage (W16A16 output network) */
+} fmd_dense_stage;
+
+/* replaces: runs of consecutive node-level layers of the reference (CFConv.lin2 -> tanh -> InteractionBlock.lin
+ * -> residual -> next CFConv.lin1, models/schnet.py:534-548,644,719; the output MLP, models/gptq.py:266-306; and
+ * the matching backward runs) by ONE launch: stage s+1 consumes the output tile of stage s from shared memory
+ * (tf32 tensor-core GEMMs as fmd_linear_tc, same numerics). X [M,K] xdt; pro_act / x_round_f16 as fmd_linear. */
+int fmd_linear_chain_tc(const void* X, int xdt, int M, int K, int pro_act, int x_round_f16,
+                        const fmd_dense_stage* stages, int n_stages, void* stream);
+
 /* ---------------------------------------------------------------- node-level helpers -------- */
 
 /* replaces: torch.nn.Embedding (models/schnet.py:203). out[i,:] = table[types[i],:]. types: idx_bytes. */
