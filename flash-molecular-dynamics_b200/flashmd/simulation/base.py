@@ -283,6 +283,9 @@ class _Simulation:
                 data, potential, forces = self.timestep(data, forces)
                 pos, vel = data[POSITIONS_KEY], data[VELOCITY_KEY] if VELOCITY_KEY in data else None
             if (t + 1) % self.save_interval == 0:
+                if eng is not None and eng.ff.w is not None and eng.ff.num_edges() > eng.ff.cap:
+                    raise RuntimeError(f"neighbour list overflow at #timestep={t}: {eng.ff.num_edges()} edges > "
+                                       f"capacity {eng.ff.cap}")
                 self.save(pos, vel, forces, potential, t)
                 if self.export_interval is not None and (t + 1) % self.export_interval == 0:
                     self.write()
