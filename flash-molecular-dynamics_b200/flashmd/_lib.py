@@ -69,6 +69,8 @@ _SIGS = {
                     c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "fmd_linear_tc": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                        c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
+    "fmd_linear_x3": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                       c_void_p, c_void_p], c_int),
     "fmd_linear_chain_tc": ([c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(DenseStage), c_int, c_void_p],
                             c_int),
     "fmd_embedding": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),

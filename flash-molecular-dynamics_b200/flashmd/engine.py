@@ -27,6 +27,7 @@ step has no host synchronisation and can be captured in a CUDA graph.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -225,6 +226,9 @@ class ForceField:
         # W16A16 with the default widths runs the fused tcgen05 kernels (no [E,F] tensor in HBM);
         # other widths / the fp32 parity path use the materialised SIMT kernels.
         self.fused_tc = (precision == "w16a16" and F == 128 and H == 128 and R <= 64 and use_tensor_cores)
+        # fp32 parity path: dense layers as fp32-accurate 3xTF32 tensor-core GEMMs (fmd_linear_x3) instead of SIMT FMA
+        self.x3 = precision == "fp32" and use_tensor_cores
+        self.x3_nodes = os.environ.get("FMD_X3_NODES", "1") == "1"     # node-level layers too (debug toggle)
         self.deg = torch.zeros(N, dtype=i32, device=dev)
         self.seg_ptr = torch.zeros(N + 1, dtype=i32, device=dev)
         self.n_edges_dev = self.seg_ptr[N:]                      # int32[1] view: live edge count
@@ -268,11 +272,19 @@ class ForceField:
         args = (L.ptr(x), L.dt_code(x), L.ptr(w), L.dt_code(w), L.ptr(bias), L.ptr(y), L.dt_code(y), M, N,
                 K, L.ptr(m_dev), kw.get("pro_act", 0), int(kw.get("x_round", False)), kw.get("epi_act", 0),
                 L.ptr(kw.get("aux")), L.dt_code(kw["aux"]) if kw.get("aux") is not None else 0, L.ptr(kw.get("res")))
+        f32 = torch.float32
+        x3 = (self.x3 and (self.x3_nodes or m_dev is not None) and x.dtype == f32 and w.dtype == f32 and y.dtype == f32 and K <= 128 and N <= 128 and K % 2 == 0
+              and not kw.get("pro_act", 0) and not kw.get("x_round", False)
+              and (kw.get("aux") is None or kw["aux"].dtype == f32) and (bias is None or bias.dtype == f32))
         if tc:
             wt = self.w.twin.get(w.data_ptr())
             if wt is not None:
                 args = args[:2] + (L.ptr(wt),) + args[3:]
             L.call("fmd_linear_tc", *args, int(wt is not None), self._st)
+        elif x3:
+            # fp32 parity path: 3xTF32 split GEMM on the tensor cores (fp32-accurate), HBM-bound streaming kernel
+            L.call("fmd_linear_x3", L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(y), M, N, K, L.ptr(m_dev),
+                   kw.get("epi_act", 0), L.ptr(kw.get("aux")), L.ptr(kw.get("res")), self._st)
         else:
             L.call("fmd_linear", *args, self._st)
         self._n += 1

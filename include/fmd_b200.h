@@ -215,6 +215,16 @@ int fmd_linear_tc(const void* X, int xdt, const void* W, int wdt, const void* bi
                   int K, const int32_t* m_dev, int pro_act, int x_round_f16, int epi_act, const void* aux, int auxdt,
                   const float* res, int w_is_nk, void* stream);
 
+/* fp32-ACCURATE variant of fmd_linear on the tensor cores ("3xTF32"): every fp32 operand is split into two TF32
+ * numbers (x = hi + lo, 22 significant bits) and lo*hi + hi*lo + hi*hi is accumulated in the fp32 TMEM accumulator.
+ * This is the GEMM of the fp32 parity path (1e-5 against the reference's --disable_optim fp32 path, models/mlp.py:41-57,
+ * models/schnet.py:534-548,644,719 and their autograd): the edge-level filter-network layers [E,R]x[R,F], [E,F]x[F,F]
+ * and their backward products, and the node-level layers.  fp32 in / fp32 out, even K <= 128, N <= 128, W row-major
+ * [K,N]; epi_act / aux / res / m_dev as fmd_linear (exact tanhf for FMD_ACT_TANH).  Streaming pipeline (HBM-bound):
+ * see csrc/fmd_linear_x3.cu. */
+int fmd_linear_x3(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K,
+                  const int32_t* m_dev, int epi_act, const float* aux, const float* res, void* stream);
+
 /* One dense layer of fmd_linear_chain_tc. W is [N,K] (the nn.Linear.weight layout), K = N of the previous stage. */
 #define FMD_MAX_CHAIN 4
 typedef struct {

@@ -244,6 +244,50 @@ def test_dense_layers_tensor_core_tf32(M, K, N):
     assert rel_l2(y.cpu(), (xh.double() @ wh.double()).cpu()) < 2e-6
 
 
+@pytest.mark.parametrize("M,K,N", [(1000, 50, 128), (34432, 128, 128), (777, 128, 50), (300, 64, 64), (5, 2, 8),
+                                   (70001, 128, 128), (513, 128, 1), (260, 100, 36)])
+def test_dense_layers_tensor_core_3xtf32(M, K, N):
+    """fmd_linear_x3 (tcgen05 kind::tf32, hi/lo split operands) is an fp32-ACCURATE GEMM: against torch fp64 it must
+    be as good as the true-fp32 FMA kernel (fmd_linear) up to a small factor, with every epilogue, ragged K / N,
+    a device-side row count, and rows beyond it left untouched."""
+    from flashmd import _lib as L
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn((M, K), generator=g).to(DEV)
+    w = (torch.randn((K, N), generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    aux = torch.tanh(torch.randn((M, N), generator=g)).to(DEV)
+    res = torch.randn((M, N), generator=g).to(DEV)
+
+    def run(b_=None, epi=0, aux_=None, res_=None, m_dev=None):
+        y = torch.full((M, N), 7.0, dtype=torch.float32, device=DEV)
+        L.call("fmd_linear_x3", L.ptr(x), L.ptr(w), L.ptr(b_), L.ptr(y), M, N, K, L.ptr(m_dev), epi, L.ptr(aux_),
+               L.ptr(res_), L.stream_ptr())
+        return y
+
+    def run_fma(b_=None, epi=0, aux_=None, res_=None):
+        y = torch.empty((M, N), dtype=torch.float32, device=DEV)
+        L.call("fmd_linear", L.ptr(x), 0, L.ptr(w), 0, L.ptr(b_), L.ptr(y), 0, M, N, K, None, 0, 0, epi, L.ptr(aux_), 0,
+               L.ptr(res_), L.stream_ptr())
+        return y
+    xd, wd = x.double(), w.double()
+    for kw, ref in ((dict(), xd @ wd),
+                    (dict(b_=b), xd @ wd + b.double()),
+                    (dict(b_=b, epi=L.ACT_TANH), torch.tanh(xd @ wd + b.double())),
+                    (dict(aux_=aux), (xd @ wd) * (1 - aux.double() ** 2)),
+                    (dict(b_=b, res_=res), xd @ wd + b.double() + res.double()),
+                    (dict(b_=b, epi=L.ACT_TANH, aux_=aux, res_=res),
+                     torch.tanh(xd @ wd + b.double()) * (1 - aux.double() ** 2) + res.double())):
+        e3 = rel_l2(run(**kw).cpu(), ref.cpu())
+        e1 = rel_l2(run_fma(**kw).cpu(), ref.cpu())
+        assert e3 < 2e-6 and e3 < 5 * e1 + 2e-7, (kw.keys(), e3, e1)
+    # device-side live row count: rows >= m_dev are not written
+    live = max(M - 37, 1)
+    md = torch.tensor([live], dtype=torch.int32, device=DEV)
+    y = run(b_=b, m_dev=md)
+    assert rel_l2(y[:live].cpu(), (xd @ wd + b.double())[:live].cpu()) < 1e-6
+    assert torch.all(y[live:] == 7.0)
+
+
 @pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz"])
 def test_schnet_fp32_vs_reference_golden(name):
     """fp32 energies and forces within 1e-5 relative of the reference's fp32 path (north star)."""
