@@ -71,6 +71,8 @@ _SIGS = {
                        c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
     "fmd_linear_x3": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                        c_void_p, c_void_p], c_int),
+    "fmd_linear_x3_rbf_bwd": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                               c_void_p, c_int, c_void_p], c_int),
     "fmd_linear_chain_tc": ([c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(DenseStage), c_int, c_void_p],
                             c_int),
     "fmd_embedding": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p], c_int),

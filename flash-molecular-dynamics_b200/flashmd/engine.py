@@ -228,7 +228,9 @@ class ForceField:
         self.fused_tc = (precision == "w16a16" and F == 128 and H == 128 and R <= 64 and use_tensor_cores)
         # fp32 parity path: dense layers as fp32-accurate 3xTF32 tensor-core GEMMs (fmd_linear_x3) instead of SIMT FMA
         self.x3 = precision == "fp32" and use_tensor_cores
-        self.x3_nodes = os.environ.get("FMD_X3_NODES", "1") == "1"     # node-level layers too (debug toggle)
+        # node-level layers stay on the true-fp32 FMA kernel by default: they are 6 % of the step and the tensor-core
+        # accumulation (round-toward-zero) leaves a coherent -1e-5 bias in the per-molecule energies (forces equal)
+        self.x3_nodes = os.environ.get("FMD_X3_NODES", "0") == "1"
         self.deg = torch.zeros(N, dtype=i32, device=dev)
         self.seg_ptr = torch.zeros(N + 1, dtype=i32, device=dev)
         self.n_edges_dev = self.seg_ptr[N:]                      # int32[1] view: live edge count
@@ -484,10 +486,16 @@ class ForceField:
             self._n += 1
             # g_t = (g_W @ f1_w[f,j]) * (1 - t^2) ; g_rbf = g_t @ f0_w[j,k]
             self._lin(self.gW, k[f"b{l}.f1_w{sfx}"], None, self.gT, m_dev=ned, aux=self.t[l])
-            self._lin(self.gT, k[f"b{l}.f0_w{sfx}"], None, self.g_rbf, m_dev=ned)
-            L.call("fmd_rbf_bwd", L.ptr(self.dist), L.ptr(self.g_rbf), None, self.cap, L.ptr(ned), L.ptr(w.centers),
-                   w.num_rbf, w.gamma, w.cutoff, L.ptr(self.g_d), 1, st)
-            self._n += 1
+            if self.x3 and w.filters <= 128 and w.filters % 2 == 0 and w.num_rbf <= 128:
+                # g_rbf = gT @ f0_w contracted with d rbf / d d in the GEMM's epilogue: [E,R] never leaves the SM
+                L.call("fmd_linear_x3_rbf_bwd", L.ptr(self.gT), L.ptr(k[f"b{l}.f0_w"]), self.cap, w.num_rbf, w.filters,
+                       L.ptr(ned), L.ptr(self.dist), L.ptr(w.centers), w.gamma, w.cutoff, L.ptr(self.g_d), 1, st)
+                self._n += 1
+            else:
+                self._lin(self.gT, k[f"b{l}.f0_w{sfx}"], None, self.g_rbf, m_dev=ned)
+                L.call("fmd_rbf_bwd", L.ptr(self.dist), L.ptr(self.g_rbf), None, self.cap, L.ptr(ned), L.ptr(w.centers),
+                       w.num_rbf, w.gamma, w.cutoff, L.ptr(self.g_d), 1, st)
+                self._n += 1
             # g_h <- g_h + g_a @ lin1_w[f,h]   (not needed below block 0: dE/dh_0 does not enter the forces)
             if l > 0:
                 self._lin(self.g_a, k[f"b{l}.lin1_w"], None, gh_nxt, res=gh_cur)

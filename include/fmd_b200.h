@@ -215,15 +215,25 @@ int fmd_linear_tc(const void* X, int xdt, const void* W, int wdt, const void* bi
                   int K, const int32_t* m_dev, int pro_act, int x_round_f16, int epi_act, const void* aux, int auxdt,
                   const float* res, int w_is_nk, void* stream);
 
-/* fp32-ACCURATE variant of fmd_linear on the tensor cores ("3xTF32"): every fp32 operand is split into two TF32
- * numbers (x = hi + lo, 22 significant bits) and lo*hi + hi*lo + hi*hi is accumulated in the fp32 TMEM accumulator.
- * This is the GEMM of the fp32 parity path (1e-5 against the reference's --disable_optim fp32 path, models/mlp.py:41-57,
- * models/schnet.py:534-548,644,719 and their autograd): the edge-level filter-network layers [E,R]x[R,F], [E,F]x[F,F]
- * and their backward products, and the node-level layers.  fp32 in / fp32 out, even K <= 128, N <= 128, W row-major
- * [K,N]; epi_act / aux / res / m_dev as fmd_linear (exact tanhf for FMD_ACT_TANH).  Streaming pipeline (HBM-bound):
- * see csrc/fmd_linear_x3.cu. */
+/* fp32-ACCURATE variant of fmd_linear on the tensor cores (fp32 emulation with three bf16 slices per operand,
+ * x = s1 + s2 + s3 exactly, six slice products accumulated in two fp32 TMEM accumulators; csrc/fmd_linear_x3.cu explains
+ * why 8-bit slices and not 3xTF32: the tensor core truncates when it accumulates, and only 16-bit products sum exactly).
+ * replaces: the dense layers of the reference's fp32 path (--disable_optim: nn.Linear / MLP, models/mlp.py:41-57,
+ * models/schnet.py:534-548,644,719, and their autograd) for the 1e-5 parity path: the edge-level filter-network layers
+ * [E,R]x[R,F], [E,F]x[F,F] and their backward products.  fp32 in / fp32 out, even K <= 128, N <= 128, W row-major
+ * [K,N]; epi_act / aux / res / m_dev as fmd_linear (exact tanhf for FMD_ACT_TANH).  Streaming pipeline, HBM-bound. */
 int fmd_linear_x3(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K,
                   const int32_t* m_dev, int epi_act, const float* aux, const float* res, void* stream);
+
+/* fmd_linear_x3 with the "rbf backward" epilogue: g_rbf = X[M,K] @ W[K,num_rbf] is never stored; row e is contracted
+ * at once with d rbf_k / d d at d_e:
+ *   g_d[e] (+)= sum_k g_rbf[e,k] * exp(gamma (d_e - mu_k)^2) * (2 gamma (d_e - mu_k) C(d_e) + C'(d_e))
+ * replaces: the last backward GEMM of the filter network (autograd of models/mlp.py:41-57) followed by the backward of
+ * FusedDistanceGaussianRBFCutoffFunction (kernels/cfconv_kernels.py:1679-1735, first half: grad_rbf -> grad_dist).
+ * Saves the [E,R] write + read and one launch per interaction block on the fp32 parity path. */
+int fmd_linear_x3_rbf_bwd(const float* X, const float* W, int M, int num_rbf, int K, const int32_t* m_dev,
+                          const float* dist, const float* centers, float gamma, float rc, float* g_d, int accumulate,
+                          void* stream);
 
 /* One dense layer of fmd_linear_chain_tc. W is [N,K] (the nn.Linear.weight layout), K = N of the previous stage. */
 #define FMD_MAX_CHAIN 4

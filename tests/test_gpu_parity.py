@@ -2,6 +2,8 @@
 the CPU oracle and the golden vectors produced by the unmodified reference.  Run on the B200 box
 with `pytest -m gpu`.  Tolerances: integer/index work bit-exact; fp32 path 1e-5 relative L2 (the
 north-star bar); W16A16 path 1e-2 relative force error."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -286,6 +288,39 @@ def test_dense_layers_tensor_core_3xtf32(M, K, N):
     y = run(b_=b, m_dev=md)
     assert rel_l2(y[:live].cpu(), (xd @ wd + b.double())[:live].cpu()) < 1e-6
     assert torch.all(y[live:] == 7.0)
+
+
+@pytest.mark.parametrize("M,K,R", [(1000, 128, 50), (70001, 128, 50), (333, 64, 20), (129, 128, 128), (64, 32, 7)])
+def test_dense_rbf_backward_fused_epilogue(M, K, R):
+    """fmd_linear_x3_rbf_bwd == fmd_linear_x3 followed by fmd_rbf_bwd (the unfused pair it replaces), and both agree
+    with the fp64 formula of the reference's fused-RBF backward (kernels/cfconv_kernels.py:1679-1735)."""
+    from flashmd import _lib as L
+    g = torch.Generator().manual_seed(M + K + R)
+    rc, gamma = 1.2, -7.5
+    x = torch.randn((M, K), generator=g).to(DEV)
+    w = (torch.randn((K, R), generator=g) / K ** 0.5).to(DEV)
+    d = (torch.rand(M, generator=g) * 1.3).to(DEV)          # some beyond the cut-off
+    mu = torch.linspace(0, rc, R).to(DEV)
+    gd0 = torch.randn(M, generator=g).to(DEV)
+    live = max(M - 11, 1)
+    md = torch.tensor([live], dtype=torch.int32, device=DEV)
+    for acc in (0, 1):
+        g1 = gd0.clone()
+        L.call("fmd_linear_x3_rbf_bwd", L.ptr(x), L.ptr(w), M, R, K, L.ptr(md), L.ptr(d), L.ptr(mu), gamma, rc, L.ptr(g1),
+               acc, L.stream_ptr())
+        grbf = torch.zeros((M, R), device=DEV)
+        L.call("fmd_linear_x3", L.ptr(x), L.ptr(w), None, L.ptr(grbf), M, R, K, L.ptr(md), 0, None, None, L.stream_ptr())
+        g2 = gd0.clone()
+        L.call("fmd_rbf_bwd", L.ptr(d), L.ptr(grbf), None, M, L.ptr(md), L.ptr(mu), R, gamma, rc, L.ptr(g2), acc, L.stream_ptr())
+        dd, xd = d.double(), x.double() @ w.double()
+        diff = dd[:, None] - mu.double()[None, :]
+        ex = torch.exp(gamma * diff * diff)
+        C = torch.where(dd < rc, 0.5 * (torch.cos(dd * math.pi / rc) + 1), torch.zeros_like(dd))
+        dC = torch.where(dd < rc, -0.5 * math.pi / rc * torch.sin(dd * math.pi / rc), torch.zeros_like(dd))
+        ref = (xd * ex * (2 * gamma * diff * C[:, None] + dC[:, None])).sum(1) + (gd0.double() if acc else 0)
+        assert rel_l2(g1[:live].cpu(), ref[:live].cpu()) < 2e-6
+        assert rel_l2(g1[:live].cpu(), g2[:live].cpu()) < 2e-6
+        assert torch.equal(g1[live:], gd0[live:])
 
 
 @pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz"])
