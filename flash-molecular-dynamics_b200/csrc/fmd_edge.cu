@@ -6,6 +6,8 @@
 //   * node rows (x [N,F], pos [N,3]) are gathered and stay L2-resident (N*F*4 = 17.6 MB at cfg2);
 //   * no atomics on the step path; reductions use fixed lane assignment + xor-shuffle trees, so
 //     results are bitwise reproducible run to run.
+#include <cstdlib>
+
 #include "fmd_common.cuh"
 
 using namespace fmd;
@@ -209,6 +211,94 @@ cfconv_csr_kernel(const float* __restrict__ x, const WT* __restrict__ filt, cons
         }
       }
       if (fa) store4(out + (size_t)i * F + f0, acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- CFConv CSR segment reduce, F = 128, list order
+// Specialisation for the layout the engine produces (F = 128, int32 CSR, no permutation): a HALF-warp per edge, lane
+// owns 8 features (one 16-byte load of an fp16 filter row / two of an fp32 row, two 16-byte loads of the gathered x
+// row), so one warp-wide load instruction moves two edges and U slots keep 2U edges in flight per warp -- the generic
+// kernel above has 4 edges (1 KB of fp16 filter) in flight per warp and sat at 48 % of the HBM roofline, latency-bound.
+// The two half-warp partial sums are combined once per node in a fixed order (deterministic).
+__device__ __forceinline__ void load8_stream(const float* p, float4& a, float4& b) {
+  a = load4_stream(p);
+  b = load4_stream(p + 4);
+}
+__device__ __forceinline__ void load8_stream(const __half* p, float4& a, float4& b) {
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  const float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+  const float2 f2 = __half22float2(*reinterpret_cast<__half2*>(&u.z)), f3 = __half22float2(*reinterpret_cast<__half2*>(&u.w));
+  a = make_float4(f0.x, f0.y, f1.x, f1.y);
+  b = make_float4(f2.x, f2.y, f3.x, f3.y);
+}
+
+template <typename WT, int U>
+__global__ void __launch_bounds__(256)
+cfconv_csr128_kernel(const float* __restrict__ x, const WT* __restrict__ filt, const float* __restrict__ dist,
+                     const int32_t* __restrict__ gather, const int32_t* __restrict__ seg_ptr, int n_nodes, int n_edges,
+                     float rc, float* __restrict__ out) {
+  constexpr int F = 128;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  const int h = lane >> 4, f0 = (lane & 15) * 8;
+  for (int i = wid; i < n_nodes; i += nw) {
+    const int a = min(seg_ptr[i], n_edges), b = min(seg_ptr[i + 1], n_edges);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int base = a; base < b; base += 32) {
+      const int p = base + lane;
+      int j_l = 0;
+      float c_l = 0.f;
+      if (p < b) {
+        j_l = gather[p];
+        c_l = cosine_cutoff(dist[p], rc);
+      }
+      const int cnt = min(32, b - base);
+      for (int k = 0; k < cnt; k += 2 * U) {
+        int j[U], e[U];
+        float c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int kk = k + 2 * u + h;
+          const bool valid = kk < cnt;
+          const int kc = valid ? kk : 0;          // past the end: edge `base` again with weight 0 (loads stay in bounds)
+          j[u] = __shfl_sync(0xffffffffu, j_l, kc);
+          const float cv = __shfl_sync(0xffffffffu, c_l, kc);
+          c[u] = valid ? cv : 0.f;
+          e[u] = base + kc;
+        }
+        float4 w0[U], w1[U], x0[U], x1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const WT* wp = filt + (size_t)e[u] * F + f0;
+          load8_stream(wp, w0[u], w1[u]);
+          const float* xp = x + (size_t)j[u] * F + f0;
+          x0[u] = load4(xp);
+          x1[u] = load4(xp + 4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          acc[0] = fmaf(x0[u].x * w0[u].x, c[u], acc[0]);
+          acc[1] = fmaf(x0[u].y * w0[u].y, c[u], acc[1]);
+          acc[2] = fmaf(x0[u].z * w0[u].z, c[u], acc[2]);
+          acc[3] = fmaf(x0[u].w * w0[u].w, c[u], acc[3]);
+          acc[4] = fmaf(x1[u].x * w1[u].x, c[u], acc[4]);
+          acc[5] = fmaf(x1[u].y * w1[u].y, c[u], acc[5]);
+          acc[6] = fmaf(x1[u].z * w1[u].z, c[u], acc[6]);
+          acc[7] = fmaf(x1[u].w * w1[u].w, c[u], acc[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
+    if (h == 0) {
+      float* o = out + (size_t)i * F + f0;
+      store4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      store4(o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
   }
 }
@@ -436,6 +526,25 @@ extern "C" int fmd_cfconv_csr(const float* x, const void* filt, int wdt, const f
   FMD_REQUIRE(n_feat > 0 && n_feat % 4 == 0, "fmd_cfconv_csr: n_feat must be a positive multiple of 4");
   if (n_nodes == 0) return FMD_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (n_feat == 128 && idx_bytes == 4 && !perm) {
+    static int u_sel = -1;   // edges in flight per warp = 2U; FMD_CSR128_U=4|8 overrides the default (tuning knob)
+    if (u_sel < 0) {
+      const char* ev = getenv("FMD_CSR128_U");
+      u_sel = ev ? atoi(ev) : 0;
+    }
+    const int grid = min(fmd_div_up((long long)n_nodes * 32, 256), fmd_num_sms() * 8);
+#define FMD_CSR128(WT, U)                                                                                          \
+  cfconv_csr128_kernel<WT, U><<<grid, 256, 0, st>>>(x, (const WT*)filt, dist, (const int32_t*)gather,                \
+                                                    (const int32_t*)seg_ptr, n_nodes, n_edges, rc, out)
+    if (wdt == FMD_F32) {
+      if (u_sel == 8) FMD_CSR128(float, 8); else FMD_CSR128(float, 4);
+    } else {
+      if (u_sel == 4) FMD_CSR128(__half, 4); else FMD_CSR128(__half, 8);
+    }
+#undef FMD_CSR128
+    FMD_CHECK_LAUNCH();
+    return FMD_OK;
+  }
   if (wdt == FMD_F32) {
     if (idx_bytes == 4) launch_cfconv<float, int32_t>(x, filt, dist, gather, seg_ptr, perm, n_nodes, n_edges, n_feat, rc, out, st);
     else launch_cfconv<float, int64_t>(x, filt, dist, gather, seg_ptr, perm, n_nodes, n_edges, n_feat, rc, out, st);
