@@ -418,11 +418,28 @@ def kernel_roofline(ff, eng, args, E):
         cf_ms = avg_ms("fmd_cfconv_csr")
         alg = E * F * b + 4 * N * F + 4 * N * F + 4 * E + 4 * E + 4 * (N + 1)
         achieved = alg / (cf_ms * 1e-3) / 1e9
-        roof = {"kernel": "cfconv_csr_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": traffic.get("cfconv_csr_kernel"),
+        kname = "cfconv_csr128_kernel<float>" if (b == 4 and F == 128) else "cfconv_csr_kernel"
+        roof = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "frac": achieved / hbm, "traffic": traffic.get(kname),
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": cf_ms,
                 "launches_per_step": len(timings.get("fmd_cfconv_csr", [])) // reps,
                 "peak_source": which + " hbm_gbs (burst copy)", "how": how}
+        if "fmd_linear_x3" in timings:
+            # fp32-emulation GEMMs of the filter network (edge level, HBM-bound streaming kernels): algorithmic bytes per
+            # interaction block = X read + Y written (+ aux read): rbf->t 4E(R+F), t->W 8EF, gW->gT 12EF, and the fused
+            # gT -> g_rbf -> g_d launch 4EF + 12E
+            nb = ff.w.num_blocks
+            alg3 = nb * (4.0 * E * (R + F) + 8.0 * E * F + 12.0 * E * F)
+            ms3 = sum(a.elapsed_time(bb) for a, bb in timings["fmd_linear_x3"]) / reps
+            n_node = sum(1 for _ in timings["fmd_linear_x3"]) // reps - 3 * nb
+            algr = nb * (4.0 * E * F + 12.0 * E)
+            msr = sum(a.elapsed_time(bb) for a, bb in timings.get("fmd_linear_x3_rbf_bwd", [])) / reps
+            roof["also"] = [{"kernel": "linear_x3_kernel (BF16x3 fp32-emulation GEMM, edge-level launches)", "bound": "hbm",
+                             "achieved": (alg3 + algr) / ((ms3 + msr) * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                             "frac": (alg3 + algr) / ((ms3 + msr) * 1e-3) / 1e9 / hbm, "traffic": traffic.get("linear_x3_kernel"),
+                             "algorithmic_bytes_per_step": alg3 + algr, "ms_per_step": ms3 + msr,
+                             "launches_per_step": 4 * nb, "node_level_launches_included_in_time": max(n_node, 0),
+                             "peak_source": which + " hbm_gbs (burst copy)", "how": how}]
     return roof, table
 
 

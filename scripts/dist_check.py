@@ -55,7 +55,8 @@ def main():
     sim = PTSimulation(friction=1.0, dt=0.004, n_timesteps=200, save_interval=10, export_interval=100,
                        exchange_interval=20, save_energies=True, random_seed=7, device=str(dev), filename="pt",
                        output_dir=out, gptq="w16a16")
-    sim.attach_model_and_configurations(model, configs[:world], betas=[1.67, 1.42, 1.16, 1.0])
+    sim.attach_model_and_configurations(model, [configs[i % len(configs)] for i in range(world)],
+                                        betas=[1.67, 1.42, 1.16, 1.0])
     assert sim.n_sims == 4 * world // world
     sim.simulate()
     m = sim.get_throughput_metrics()
