@@ -187,23 +187,56 @@ def _oracle_priors(sysd, B):
     return out
 
 
+def cpu_reference_throughput(args, n_mols, n_steps, threads):
+    """The UNMODIFIED reference (pip-installed into baseline/_ref, imported behind oracle/shims) on the host cores with
+    its --disable_optim semantics (MLCG_*=0, gptq=None, no compile: scripts/nvt_langevin.py:6-17,40-60), in a
+    subprocess because its package name clashes with the drop-in.  Timed with the reference's own second-half
+    throughput metric (simulation/base.py:748-787) over 2*n_steps timesteps.  None when baseline/_ref is absent."""
+    import subprocess
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "flashmd")) or args.blocks != 3:
+        return None
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_triton_reference.py"), "--device", "cpu", "--batch",
+           str(n_mols), "--n-beads", str(args.n_beads), "--steps", str(2 * n_steps), "--threads", str(threads)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        rec = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        m = rec["metrics"]
+        return float(m["throughput"]), float(m["second_half_elapsed_time"]), int(m["second_half_steps"]), int(rec["threads"])
+    except Exception as e:  # noqa: BLE001  (fall back to the port, say why)
+        print(f"[bench] reference CPU run failed ({e!r}); falling back to the oracle port", file=sys.stderr)
+        return None
+
+
+def cpu_baseline_entry(args, n_mols, n_steps):
+    """cpu_baseline object: the reference itself when it is installed (kind "reference"), else the oracle port."""
+    cores = os.cpu_count() or 1
+    ref = cpu_reference_throughput(args, n_mols, n_steps, cores)
+    if ref is not None:
+        val, secs, steps, thr = ref
+        return {"value": val, "unit": UNIT, "cores": thr, "kind": "reference",
+                "sample": f"{n_mols} molecules x {args.n_beads} beads, second half ({steps} BAOAB steps, {secs:.1f} s) of a "
+                          f"{2 * steps}-step run of the UNMODIFIED reference (baseline/_ref) with --disable_optim semantics "
+                          f"(MLCG_*=0, gptq=None, no compile) on {thr} host threads; torch_cluster.radius_graph served by "
+                          f"the oracle/shims stand-in"}, val, secs, steps
+    cpu_oracle_throughput(args, n_mols, 1, cores)     # warm-up (thread pool, allocator)
+    val, secs = cpu_oracle_throughput(args, n_mols, n_steps, cores)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_mols} molecules x {args.n_beads} beads, {n_steps} BAOAB steps ({secs:.1f} s), oracle port of the "
+                      f"reference's --disable_optim fp32 PyTorch path (oracle/fmd_oracle.py), {cores} threads"}, val, secs, n_steps
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    n_mols, per_step = 16, 1
-    steps, warm = max(1, min(args.steps, 20)), max(0, min(args.warmup, 2))
-    if warm:
-        cpu_oracle_throughput(args, n_mols, warm, cores)
-    val, secs = cpu_oracle_throughput(args, n_mols, steps * per_step, cores)
-    sample = (f"{n_mols} molecules x {args.n_beads} beads, {steps} BAOAB steps, oracle port of the reference's "
-              f"--disable_optim fp32 PyTorch path (oracle/fmd_oracle.py), {cores} threads")
+    n_mols = 16
+    steps, warm = max(1, min(args.steps, 10)), max(0, min(args.warmup, 2))
+    cb, val, secs, steps = cpu_baseline_entry(args, n_mols, steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": cb,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -334,14 +367,7 @@ def main():
             "roofline": roof, "kernels_ms_per_step": kern_table,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            nm, ns = 16, 24
-            cpu_oracle_throughput(args, nm, 1, cores)     # warm-up (thread pool, allocator)
-            val, secs = cpu_oracle_throughput(args, nm, ns, cores)
-            line["cpu_baseline"] = {
-                "value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{nm} molecules x {n} beads, {ns} BAOAB steps ({secs:.1f} s), oracle port of the reference's "
-                          f"--disable_optim fp32 PyTorch path (oracle/fmd_oracle.py), {cores} threads"}
+            line["cpu_baseline"] = cpu_baseline_entry(args, 16, 8)[0]
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -32,15 +32,27 @@ ap.add_argument("--n-beads", type=int, default=269)
 ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--gptq", default="w16a16")
 ap.add_argument("--compile", type=int, default=0)
+ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
+                help="cpu = the reference's --disable_optim path (MLCG_*=0, gptq=None, no compile) on the host cores")
+ap.add_argument("--threads", type=int, default=0)
 args = ap.parse_args()
+CPU = args.device == "cpu"
+if CPU:
+    # scripts/nvt_langevin.py:6-17 (--disable_optim): every MLCG_* toggle off BEFORE flashmd is imported
+    for k in ("MLCG_USE_TRITON_MESSAGE_PASSING", "MLCG_USE_FUSED_RBF", "MLCG_USE_FUSED_TANH_LINEAR", "MLCG_USE_CSR",
+              "MLCG_USE_SRC_CSR_GRAD_X"):
+        os.environ[k] = "0"
+    args.gptq, args.compile = "none", 0
+    torch.set_num_threads(args.threads or (os.cpu_count() or 1))
 
 # ---- torch_cluster stand-in backed by libfmd_b200.so (raw ctypes: the drop-in package must not be imported here,
 #      it has the same top-level name as the reference)
-_lib = ctypes.CDLL(os.path.join(ROOT, "flash-molecular-dynamics_b200", "csrc", "libfmd_b200.so"))
+_lib = None if CPU else ctypes.CDLL(os.path.join(ROOT, "flash-molecular-dynamics_b200", "csrc", "libfmd_b200.so"))
 vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
-_lib.fmd_nl_count.argtypes = [vp, vp, ci, ci, ci, cf, ci, vp, vp]
-_lib.fmd_exclusive_scan_i32.argtypes = [vp, vp, ci, vp, vp]
-_lib.fmd_nl_fill.argtypes = [vp, vp, ci, ci, ci, cf, ci, vp, ci, vp, vp, ci, vp, vp]
+if not CPU:
+  _lib.fmd_nl_count.argtypes = [vp, vp, ci, ci, ci, cf, ci, vp, vp]
+  _lib.fmd_exclusive_scan_i32.argtypes = [vp, vp, ci, vp, vp]
+  _lib.fmd_nl_fill.argtypes = [vp, vp, ci, ci, ci, cf, ci, vp, ci, vp, vp, ci, vp, vp]
 
 
 def radius_graph_cuda(x, r, batch=None, loop=False, max_num_neighbors=32, flow="source_to_target", num_workers=1,
@@ -68,8 +80,9 @@ def radius_graph_cuda(x, r, batch=None, loop=False, max_num_neighbors=32, flow="
     return ei if flow == "target_to_source" else ei.flip(0)
 
 
-import torch_cluster  # noqa: E402  (the shim)
-torch_cluster.radius_graph = radius_graph_cuda
+import torch_cluster  # noqa: E402  (the shim; on the CPU its masked-distance radius_graph is used as is)
+if not CPU:
+    torch_cluster.radius_graph = radius_graph_cuda
 
 import importlib.util  # noqa: E402
 spec = importlib.util.spec_from_file_location("fmd_synthetic", os.path.join(ROOT, "flash-molecular-dynamics_b200", "flashmd", "synthetic.py"))
@@ -81,7 +94,7 @@ assert "baseline/_ref" in flashmd.__file__, flashmd.__file__
 import flashmd.kernels.cfconv_kernels as _ck  # noqa: E402
 _ck.math = math
 import flashmd.neighbor_list.torch_impl as _ti  # noqa: E402
-if hasattr(_ti, "radius_graph"):
+if hasattr(_ti, "radius_graph") and not CPU:
     _ti.radius_graph = radius_graph_cuda
 from flashmd.data import AtomicData  # noqa: E402
 from flashmd.models import CosineCutoff, GaussianBasis, GradientsOut, StandardSchNet, SumOut  # noqa: E402
@@ -129,7 +142,7 @@ for b in range(B):
 tmp = tempfile.mkdtemp()
 gptq = None if args.gptq.lower() == "none" else args.gptq
 sim = LangevinSimulation(friction=1.0, dt=0.004, n_timesteps=args.steps, save_interval=args.steps, export_interval=args.steps,
-                         random_seed=103838, device="cuda", dtype="single", filename="ref", output_dir=tmp,
+                         random_seed=103838, device=args.device, dtype="single", filename="ref", output_dir=tmp,
                          specialize_priors=True, compile_model=bool(args.compile), gptq=gptq)
 t0 = time.perf_counter()
 sim.attach_model_and_configurations(model, configs, beta=1.67)
@@ -138,8 +151,9 @@ t0 = time.perf_counter()
 sim.simulate()
 t_sim = time.perf_counter() - t0
 m = sim.get_throughput_metrics()
-out = {"impl": "reference-triton", "gptq": gptq, "compile_model": bool(args.compile), "batch": B, "n_beads": n,
+out = {"impl": "reference-cpu-disable_optim" if CPU else "reference-triton", "threads": torch.get_num_threads(), "gptq": gptq, "compile_model": bool(args.compile), "batch": B, "n_beads": n,
        "steps": args.steps, "attach_s": t_attach, "simulate_s": t_sim,
-       "notes": "radius_graph = our CUDA kernel (torch_cluster absent); math injected into cfconv_kernels; TF32 matmul",
+       "notes": ("unmodified reference, --disable_optim semantics; torch_cluster.radius_graph = oracle/shims stand-in"
+                 if CPU else "radius_graph = our CUDA kernel (torch_cluster absent); math injected into cfconv_kernels; TF32 matmul"),
        "metrics": {k: (float(v) if isinstance(v, (int, float, np.floating)) else str(v)) for k, v in (m or {}).items()}}
 print(json.dumps(out))
