@@ -239,7 +239,14 @@ __device__ __forceinline__ float4 load4_dt(const void* p, size_t idx, int dt) {
 }
 __device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
 
-__global__ void __launch_bounds__(LT_THREADS, 1)
+// The chain kernel runs ONE iteration per CTA (269 row tiles on 148 SMs) with long dependent per-thread instruction
+// streams (ncu: IPC 0.9 per SM with 8 warps, the loads-in-flight depth makes no difference), so thread-level parallelism is
+// what it lacks: 256 threads per tile (two warps per TMEM lane quarter, each draining half of the accumulator columns),
+// 512 per CTA.
+constexpr int CH_GROUP = 256;
+constexpr int CH_THREADS = CH_GROUP * LT_GROUPS;
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
 linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int pro_act, int x_round_f16,
                        const __grid_constant__ ChainArgs ca) {
   extern __shared__ uint8_t smem_raw[];
@@ -247,9 +254,11 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   const uint32_t sbase = smem_u32(smem);
   const int tid_all = threadIdx.x, warp_all = tid_all >> 5;
-  const int group = tid_all >> 7;
-  const int tid = tid_all & (LT_TILE - 1);
-  const int warp = tid >> 5;
+  const int group = tid_all >> 8;
+  const int tid = tid_all & (CH_GROUP - 1);      // thread inside the group
+  const int warp = tid >> 5;                     // 0..7: TMEM lane quarter warp & 3, accumulator column half warp >> 2
+  const int row = (warp & 3) * 32 + (tid & 31);  // accumulator row drained by this thread
+  const int chalf = warp >> 2;
   float* sBias = reinterpret_cast<float*>(smem + LO_BIAS);
   const uint32_t bar = sbase + LO_BAR + 8u * group;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + LO_BAR + 16);
@@ -269,7 +278,7 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem = tmem_base + group * 128;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
   const uint64_t dA = smem_desc_sw128(sbase + LO_A + group * (64 * 1024), 16, 1024);
   const uint64_t dB = smem_desc_sw128(sbase + LO_B, 16, 1024);
   uint32_t it = 0;
@@ -279,18 +288,18 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
     {
       const int kc = K0 >> 2, kc_shift = (K0 == 128) ? 5 : 4;
       const int total = LT_TILE << kc_shift;
-      for (int base = 0; base < total; base += LT_TILE * 8) {
+      for (int base = 0; base < total; base += CH_GROUP * 8) {
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int idx = base + u * LT_TILE + tid;
+          const int idx = base + u * CH_GROUP + tid;
           const int r = idx >> kc_shift, c = idx & (kc - 1);
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (m0 + r < M) v[u] = load4_dt(X, (size_t)(m0 + r) * K0 + c * 4, xdt);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int idx = base + u * LT_TILE + tid;
+          const int idx = base + u * CH_GROUP + tid;
           const int r = idx >> kc_shift, c = idx & (kc - 1);
           float4 t = v[u];
           if (x_round_f16) { t.x = round_h(t.x); t.y = round_h(t.y); t.z = round_h(t.z); t.w = round_h(t.w); }
@@ -310,17 +319,17 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
       {
         const int kc = K >> 2, kc_shift = (K == 128) ? 5 : 4;
         const int total = N << kc_shift;
-        for (int base = 0; base < total; base += LT_THREADS * 8) {
+        for (int base = 0; base < total; base += CH_THREADS * 8) {
           float4 v[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * LT_THREADS + tid_all;
+            const int idx = base + u * CH_THREADS + tid_all;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (idx < total) v[u] = load4_dt(S.W, (size_t)idx * 4, S.wdt);
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * LT_THREADS + tid_all;
+            const int idx = base + u * CH_THREADS + tid_all;
             const int n = idx >> kc_shift, c = idx & (kc - 1);
             float4 t = v[u];
             t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
@@ -354,7 +363,7 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
       //     this epilogue 5x slower than the GEMM itself); the tile is rewritten as the TF32 operand of the next stage.
       const bool feed = s + 1 < ca.n_stages;
       const bool post = S.aux || S.res || S.Y;
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      for (int c0 = chalf * (N >> 1); c0 < (chalf + 1) * (N >> 1); c0 += 32) {
         uint32_t rr[32];
         tmem_ld32(tmem + lane_sel + c0, rr);
         tmem_ld_wait();
@@ -372,18 +381,18 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
             v[0] = to_tf32(v[0]); v[1] = to_tf32(v[1]); v[2] = to_tf32(v[2]); v[3] = to_tf32(v[3]);
           }
           const int c = (c0 >> 2) + q;
-          *reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(tid, c & 7)) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(row, c & 7)) = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
       if (post) {
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(LT_TILE) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(CH_GROUP) : "memory");
         const int nc = N >> 2, nc_shift = (N == 128) ? 5 : 4;
         const int total = LT_TILE << nc_shift;
-        for (int base = 0; base < total; base += LT_TILE * 8) {
+        for (int base = 0; base < total; base += CH_GROUP * 8) {
           float4 av[8], rv[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * LT_TILE + tid;
+            const int idx = base + u * CH_GROUP + tid;
             const int r = idx >> nc_shift, c = idx & (nc - 1);
             const size_t o = (size_t)(m0 + r) * N + c * 4;
             const bool ok = m0 + r < M;
@@ -392,7 +401,7 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * LT_TILE + tid;
+            const int idx = base + u * CH_GROUP + tid;
             const int r = idx >> nc_shift, c = idx & (nc - 1);
             float4* slot = reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(r, c & 7));
             float4 v = *slot;
@@ -487,7 +496,7 @@ extern "C" int fmd_linear_chain_tc(const void* X, int xdt, int M, int K, int pro
   }
   const int pairs = fmd_div_up(fmd_div_up(M, LT_TILE), LT_GROUPS);
   const int grid = pairs < fmd_num_sms() ? pairs : fmd_num_sms();
-  linear_chain_tc_kernel<<<grid, LT_THREADS, LT_SMEM_ALLOC, (cudaStream_t)stream>>>(X, xdt, M, K, pro_act, x_round_f16, ca);
+  linear_chain_tc_kernel<<<grid, CH_THREADS, LT_SMEM_ALLOC, (cudaStream_t)stream>>>(X, xdt, M, K, pro_act, x_round_f16, ca);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

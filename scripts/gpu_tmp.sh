@@ -1,1 +1,7 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29534 scripts/dist_check.py 2>&1 | grep "dist_check\|Error\|error" | head -8 | tee gpurun_out/dist_check_n8.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "dense or chain or w16 or tensor or fused" 2>&1 | tail -2
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_chain.json 2> gpurun_out/bench_chain.err; echo "rc=$?"
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/bench_chain.json")); print(round(d["value"]), "timestep*mol/s", round(d["ms_per_step"],3), "ms/step  e2e", round(d["e2e"]["value"]))
+for k,v in d["kernels_ms_per_step"].items(): print(" ", k, round(v["ms_per_step"],3), v["launches_per_step"])
+PY
