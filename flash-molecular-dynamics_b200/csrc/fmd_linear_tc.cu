@@ -243,7 +243,7 @@ __device__ __forceinline__ float round_h(float v) { return __half2float(__float2
 // streams (ncu: IPC 0.9 per SM with 8 warps, the loads-in-flight depth makes no difference), so thread-level parallelism is
 // what it lacks: 256 threads per tile (two warps per TMEM lane quarter, each draining half of the accumulator columns),
 // 512 per CTA.
-constexpr int CH_GROUP = 256;
+constexpr int CH_GROUP = 512;
 constexpr int CH_THREADS = CH_GROUP * LT_GROUPS;
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
@@ -254,11 +254,12 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   const uint32_t sbase = smem_u32(smem);
   const int tid_all = threadIdx.x, warp_all = tid_all >> 5;
-  const int group = tid_all >> 8;
+  const int group = tid_all / CH_GROUP;
   const int tid = tid_all & (CH_GROUP - 1);      // thread inside the group
-  const int warp = tid >> 5;                     // 0..7: TMEM lane quarter warp & 3, accumulator column half warp >> 2
+  const int warp = tid >> 5;                     // TMEM lane quarter warp & 3, accumulator column slice warp >> 2
   const int row = (warp & 3) * 32 + (tid & 31);  // accumulator row drained by this thread
-  const int chalf = warp >> 2;
+  constexpr int CSL = CH_GROUP / 128;            // column slices (warps per lane quarter)
+  const int cslice = warp >> 2;
   float* sBias = reinterpret_cast<float*>(smem + LO_BIAS);
   const uint32_t bar = sbase + LO_BAR + 8u * group;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + LO_BAR + 16);
@@ -288,17 +289,17 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
     {
       const int kc = K0 >> 2, kc_shift = (K0 == 128) ? 5 : 4;
       const int total = LT_TILE << kc_shift;
-      for (int base = 0; base < total; base += CH_GROUP * 8) {
-        float4 v[8];
+      for (int base = 0; base < total; base += CH_GROUP * 4) {
+        float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
           const int idx = base + u * CH_GROUP + tid;
           const int r = idx >> kc_shift, c = idx & (kc - 1);
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (m0 + r < M) v[u] = load4_dt(X, (size_t)(m0 + r) * K0 + c * 4, xdt);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
           const int idx = base + u * CH_GROUP + tid;
           const int r = idx >> kc_shift, c = idx & (kc - 1);
           float4 t = v[u];
@@ -319,16 +320,16 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
       {
         const int kc = K >> 2, kc_shift = (K == 128) ? 5 : 4;
         const int total = N << kc_shift;
-        for (int base = 0; base < total; base += CH_THREADS * 8) {
-          float4 v[8];
+        for (int base = 0; base < total; base += CH_THREADS * 4) {
+          float4 v[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 4; ++u) {
             const int idx = base + u * CH_THREADS + tid_all;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (idx < total) v[u] = load4_dt(S.W, (size_t)idx * 4, S.wdt);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 4; ++u) {
             const int idx = base + u * CH_THREADS + tid_all;
             const int n = idx >> kc_shift, c = idx & (kc - 1);
             float4 t = v[u];
@@ -363,12 +364,13 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
       //     this epilogue 5x slower than the GEMM itself); the tile is rewritten as the TF32 operand of the next stage.
       const bool feed = s + 1 < ca.n_stages;
       const bool post = S.aux || S.res || S.Y;
-      for (int c0 = chalf * (N >> 1); c0 < (chalf + 1) * (N >> 1); c0 += 32) {
-        uint32_t rr[32];
-        tmem_ld32(tmem + lane_sel + c0, rr);
+      const int cw = N / CSL;                      // columns per slice (multiple of 16)
+      for (int c0 = cslice * cw; c0 < (cslice + 1) * cw; c0 += 16) {
+        uint32_t rr[16];
+        tmem_ld16(tmem + lane_sel + c0, rr);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           float v[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(rr[q * 4 + u]) + sBias[c0 + q * 4 + u];
@@ -388,10 +390,10 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
         asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(CH_GROUP) : "memory");
         const int nc = N >> 2, nc_shift = (N == 128) ? 5 : 4;
         const int total = LT_TILE << nc_shift;
-        for (int base = 0; base < total; base += CH_GROUP * 8) {
-          float4 av[8], rv[8];
+        for (int base = 0; base < total; base += CH_GROUP * 4) {
+          float4 av[4], rv[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 4; ++u) {
             const int idx = base + u * CH_GROUP + tid;
             const int r = idx >> nc_shift, c = idx & (nc - 1);
             const size_t o = (size_t)(m0 + r) * N + c * 4;
@@ -400,7 +402,7 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
             rv[u] = (S.res && ok) ? load4(S.res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 4; ++u) {
             const int idx = base + u * CH_GROUP + tid;
             const int r = idx >> nc_shift, c = idx & (nc - 1);
             float4* slot = reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(r, c & 7));
