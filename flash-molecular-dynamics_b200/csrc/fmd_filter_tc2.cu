@@ -27,13 +27,24 @@ __device__ __forceinline__ void trace_stamp(int role, int tile, int k, bool lead
   if (g_trace != nullptr && blockIdx.x == 0 && leader && tile < 64)
     g_trace[(role * 64 + tile) * 3 + k] = (unsigned long long)clock64();
 }
+// gathered element = *(base + byte_off): ONE 32x32+64 multiply-add forms the 64-bit address (the compiler's own sequence for
+// `base + element_offset` was IADD3 + IMAD.X + LEA + LEA.HI.X per element, 4 of the 5 instructions of every gathered
+// element and 20 % of all instructions of the forward kernel)
+__device__ __forceinline__ float ldg_byte_off(const float* base, uint32_t byte_off) {
+  uint64_t addr;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(byte_off), "l"(base));
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+  return v;
+}
+
 constexpr int META_STAGES = 4;
 
 constexpr uint32_t O_WF0 = 0;                                // 16 KB
 constexpr uint32_t O_WF1 = O_WF0 + 128 * 128;                // 32 KB
 constexpr uint32_t O_RBF = O_WF1 + 2 * 128 * 128;            // 2 x 16 KB
 constexpr uint32_t O_TT = O_RBF + 2 * 128 * 128;             // 2 x 32 KB
-constexpr uint32_t O_XOFF = O_TT + 2 * 2 * 128 * 128;        // 4 x 512 B: element offset nbr*NF of the gathered row
+constexpr uint32_t O_XOFF = O_TT + 2 * 2 * 128 * 128;        // 4 x 512 B: BYTE offset nbr*NF*4 of the gathered row
 constexpr uint32_t O_CUT = O_XOFF + META_STAGES * TILE * 4;  // 4 x 512 B: C(d_e)
 constexpr uint32_t O_OWN = O_CUT + META_STAGES * TILE * 4;   // 4 x 512 B: segment owner per edge
 constexpr uint32_t O_HEAD = O_OWN + META_STAGES * TILE * 4;  // 4 x 32 B: {prev_owner, -, -, -, boundary mask[4]}
@@ -132,7 +143,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_wait_guard(bar(B_META_EMPTY + ms), mph ^ 1);
       mbar_wait_guard(bar(B_RBF_EMPTY + s), ph ^ 1);
       trace_stamp(0, i, 1, tid == 0);
-      reinterpret_cast<uint32_t*>(smem + O_XOFF + ms * TILE * 4)[tid] = (uint32_t)nb * (uint32_t)NF;
+      reinterpret_cast<uint32_t*>(smem + O_XOFF + ms * TILE * 4)[tid] = (uint32_t)nb * (uint32_t)(NF * 4);
       reinterpret_cast<float*>(smem + O_CUT + ms * TILE * 4)[tid] = cut;
       reinterpret_cast<int*>(smem + O_OWN + ms * TILE * 4)[tid] = own;
       if (tid == 0) *reinterpret_cast<int*>(smem + O_HEAD + ms * 32) = prev;
@@ -248,10 +259,10 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const uint4 o = sOff4[c16 * 4 + u];
-          xv[4 * u] = __ldg(xf + o.x);
-          xv[4 * u + 1] = __ldg(xf + o.y);
-          xv[4 * u + 2] = __ldg(xf + o.z);
-          xv[4 * u + 3] = __ldg(xf + o.w);
+          xv[4 * u] = ldg_byte_off(xf, o.x);
+          xv[4 * u + 1] = ldg_byte_off(xf, o.y);
+          xv[4 * u + 2] = ldg_byte_off(xf, o.z);
+          xv[4 * u + 3] = ldg_byte_off(xf, o.w);
         }
       };
       trace_stamp(2 + g, i, 0, f == 0);
@@ -473,7 +484,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_wait_guard(bar(C_RBF_EMPTY + s), ph ^ 1);
       trace_stamp(0, i, 1, tid == 0);
       reinterpret_cast<uint2*>(smem + BO_META + ms * TILE * 8)[tid] =
-          make_uint2((uint32_t)nb * (uint32_t)NF, __float_as_uint(cut));
+          make_uint2((uint32_t)nb * (uint32_t)(NF * 4), __float_as_uint(cut));   // byte offset of the gathered row
       reinterpret_cast<int*>(smem + BO_OWN + ms * TILE * 4)[tid] = valid ? own : 0;
       if (lane == 0) reinterpret_cast<uint32_t*>(smem + BO_HEAD + ms * 16)[warp] = bmask;
       write_rbf_row_fast(smem + BO_RBF + s * (128 * 128), sCen, tid, d, cut, g2);
@@ -549,7 +560,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       uint8_t* sOp = smem + BO_OP + g * (2 * 128 * 128);
       trace_stamp(2 + g, i, 0, f == 0);
       mbar_wait_guard(bar(C_META_FULL + ms), mph);
-      float gm = __ldg(gmf + (size_t)sOwn[0] * NF);
+      float gm = ldg_byte_off(gmf, (uint32_t)sOwn[0] * (uint32_t)(NF * 4));
       // Two half-tiles of 64 edges: all 64 row gathers of a half are in flight at once (the latency of the L2
       // gathers is paid twice per tile instead of once per 16 rows: 8.6k -> ~4k cycles in the timeline trace); the
       // first half is issued before the operand buffer is even free.
@@ -558,8 +569,8 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
           const uint4 m = sMeta2[h * 32 + u];
-          av[2 * u] = __ldg(af + m.x);
-          av[2 * u + 1] = __ldg(af + m.z);
+          av[2 * u] = ldg_byte_off(af, m.x);
+          av[2 * u + 1] = ldg_byte_off(af, m.z);
         }
       };
       auto emit64 = [&](int h) {
@@ -575,7 +586,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
             } else {
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                if ((bits >> (8 * q + u)) & 1u) gm = __ldg(gmf + (size_t)sOwn[h * 64 + w * 32 + q * 8 + u] * NF);
+                if ((bits >> (8 * q + u)) & 1u) gm = ldg_byte_off(gmf, (uint32_t)sOwn[h * 64 + w * 32 + q * 8 + u] * (uint32_t)(NF * 4));
                 v[u] *= gm;
               }
             }
@@ -739,6 +750,7 @@ extern "C" int fmd_filter_cfconv_fwd2(const float* dist, const int32_t* edge_own
   FMD_REQUIRE(dist && edge_owner && edge_nbr && seg_ptr && wf0_h && wf1_h && centers && x && out && part,
               "fmd_filter_cfconv_fwd2: null argument");
   FMD_REQUIRE(n_feat == NF && num_rbf > 0 && num_rbf <= RP, "fmd_filter_cfconv_fwd2: needs F == 128 and num_rbf <= 64");
+  FMD_REQUIRE(n_nodes < (1 << 23), "fmd_filter_cfconv_fwd2: gathered rows are addressed with 32-bit byte offsets (< 2^23 nodes)");
   if (n_nodes <= 0) return FMD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_done = false;

@@ -227,7 +227,7 @@ class ForceField:
         # other widths / the fp32 parity path use the materialised SIMT kernels.
         self.fused_tc = (precision == "w16a16" and F == 128 and H == 128 and R <= 64 and use_tensor_cores)
         # fp32 parity path: dense layers as fp32-accurate 3xTF32 tensor-core GEMMs (fmd_linear_x3) instead of SIMT FMA
-        self.x3 = precision == "fp32" and use_tensor_cores
+        self.x3 = precision == "fp32" and use_tensor_cores and os.environ.get("FMD_X3", "1") == "1"
         # node-level layers stay on the true-fp32 FMA kernel by default: they are 6 % of the step and the tensor-core
         # accumulation (round-toward-zero) leaves a coherent -1e-5 bias in the per-molecule energies (forces equal)
         self.x3_nodes = os.environ.get("FMD_X3_NODES", "0") == "1"
@@ -591,9 +591,11 @@ class LangevinEngine:
 
     def _capture(self):
         # warm-up on a side stream (allocations, lazy module loads), then capture one step
+        # the state is saved BEFORE the side stream's wait point: clones enqueued after s.wait_stream() would race with
+        # the warm-up step (the restored state was then a partially advanced one, different from run to run)
+        saved = (self.pos.clone(), self.vel.clone(), self.ff.forces.clone(), self.step_dev.clone())
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
-        saved = (self.pos.clone(), self.vel.clone(), self.ff.forces.clone(), self.step_dev.clone())
         with torch.cuda.stream(s):
             self._step_body()
         torch.cuda.current_stream().wait_stream(s)

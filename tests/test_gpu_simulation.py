@@ -181,22 +181,57 @@ def test_trajectory_statistics_vs_reference_10k_steps(gptq):
     assert abs(rg_our.mean() / rg_ref.mean() - 1.0) < 0.05, (rg_our.mean(), rg_ref.mean())
 
 
-@pytest.mark.parametrize("gptq,tol", [(None, 2e-4), ("w16a16", 2e-3)])
-def test_nve_energy_conservation_fused_engine(gptq, tol):
+@pytest.mark.parametrize("gptq,drift_bar,slope_bar", [(None, 2e-3, 1e-3), ("w16a16", 5e-3, 3e-3)])
+def test_nve_energy_conservation_fused_engine(gptq, drift_bar, slope_bar):
     """Velocity Verlet through the fused engine: total energy is conserved, which checks that the analytic
-    forces are the gradient of the energy the kernels report."""
+    forces are the gradient of the energy the kernels report.
+    Initial velocities are pinned (seeded CPU generator): attach draws them from the global RNG like the reference,
+    and the size of the integration error depends strongly on the initial condition (close repulsive contacts): with
+    the TRUE-fp32 FMA GEMMs the drift at dt = 0.001 is 1e-4 ... 2e-2 of the mean kinetic energy over five seeds, and it
+    vanishes with the time step (seed 100: 1.8e-2, 7.7e-3, 8e-4 at dt, dt/2, dt/4; scripts/dbg_nve.py, dbg_nve2.py),
+    which is the signature of integrator error, not of inconsistent forces.  The test therefore runs at dt/4."""
     from flashmd.simulation import NVESimulation
     g = load_golden("schnet_n54_b4.npz")
+    for seed in (100, 103):
+        model, _, configs = dropin_model_from_golden(g)
+        sim = NVESimulation(dt=0.00025, n_timesteps=8000, save_interval=80, save_energies=True, random_seed=1, device=DEV,
+                            gptq=gptq)
+        sim.attach_model_and_configurations(model, configs, beta=1.67)
+        d = sim.initial_data
+        gen = torch.Generator().manual_seed(seed)
+        d.velocities = (torch.randn(d.pos.shape, generator=gen) * torch.sqrt(1.0 / (1.67 * d.masses.cpu()))[:, None]).to(d.pos.device)
+        sim.simulate()
+        assert sim.get_throughput_metrics()["path"] == "fused-engine"
+        e_tot = sim.simulated_potential + sim.simulated_kinetic_energies      # [n_sims, frames]
+        ke_scale = sim.simulated_kinetic_energies.mean()
+        drift = np.abs(e_tot - e_tot[:, :1]).max() / ke_scale
+        assert drift < drift_bar, (seed, drift)     # bounded fluctuation of the shadow Hamiltonian
+        slope = np.abs(e_tot[:, -10:].mean(axis=1) - e_tot[:, :10].mean(axis=1)).max() / ke_scale
+        assert slope < slope_bar, (seed, slope)     # no systematic drift
+
+
+def test_fused_engine_graph_path_is_reproducible():
+    """Two fresh engines from identical inputs give bitwise identical trajectories through the CUDA-graph path (the
+    state saved around the capture used to race with the warm-up step)."""
+    from copy import deepcopy
+    from flashmd.engine import LangevinEngine
+    from flashmd.simulation import LangevinSimulation
+    from flashmd.simulation.lowering import lower
+    g = load_golden("schnet_n54_b4.npz")
     model, _, configs = dropin_model_from_golden(g)
-    torch.manual_seed(3)
-    sim = NVESimulation(dt=0.001, n_timesteps=2000, save_interval=20, save_energies=True, random_seed=1, device=DEV,
-                        gptq=gptq)
-    sim.attach_model_and_configurations(model, configs, beta=1.67)
-    sim.simulate()
-    assert sim.get_throughput_metrics()["path"] == "fused-engine"
-    e_tot = sim.simulated_potential + sim.simulated_kinetic_energies      # [n_sims, frames]
-    ke_scale = sim.simulated_kinetic_energies.mean()
-    drift = np.abs(e_tot - e_tot[:, :1]).max() / ke_scale
-    assert drift < tol * 50, drift          # bounded fluctuation of the shadow Hamiltonian, no systematic drift
-    slope = np.abs(e_tot[:, -10:].mean(axis=1) - e_tot[:, :10].mean(axis=1)).max() / ke_scale
-    assert slope < tol * 25, slope
+    model = model.to(DEV)
+    data = LangevinSimulation.collate(deepcopy(configs)).to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    vel = (torch.randn(data.pos.shape, generator=gen) * torch.sqrt(1.0 / (1.67 * data.masses.cpu()))[:, None]).to(DEV)
+    for prec in ("fp32", "w16a16"):
+        outs = []
+        for rep in range(3):
+            junk = torch.randn(16 * 1024 * 1024, device=DEV)   # dirty the allocator's free blocks between runs
+            del junk
+            ff = lower(model, data, prec, True)
+            eng = LangevinEngine(ff, data.pos, vel, data.masses, torch.full((4,), 1.67), 0.004, 1.0, seed=11, use_graph=True)
+            eng.run(25)
+            torch.cuda.synchronize()
+            outs.append((eng.pos.clone(), eng.vel.clone(), ff.energy.clone()))
+        for o in outs[1:]:
+            assert all(torch.equal(a, b) for a, b in zip(outs[0], o)), prec
