@@ -34,7 +34,7 @@ __device__ __forceinline__ float ldg_byte_off(const float* base, uint32_t byte_o
   uint64_t addr;
   asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(byte_off), "l"(base));
   float v;
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+  asm("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(addr));
   return v;
 }
 
@@ -484,7 +484,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_wait_guard(bar(C_RBF_EMPTY + s), ph ^ 1);
       trace_stamp(0, i, 1, tid == 0);
       reinterpret_cast<uint2*>(smem + BO_META + ms * TILE * 8)[tid] =
-          make_uint2((uint32_t)nb * (uint32_t)(NF * 4), __float_as_uint(cut));   // byte offset of the gathered row
+          make_uint2((uint32_t)nb * (uint32_t)NF, __float_as_uint(cut));
       reinterpret_cast<int*>(smem + BO_OWN + ms * TILE * 4)[tid] = valid ? own : 0;
       if (lane == 0) reinterpret_cast<uint32_t*>(smem + BO_HEAD + ms * 16)[warp] = bmask;
       write_rbf_row_fast(smem + BO_RBF + s * (128 * 128), sCen, tid, d, cut, g2);
@@ -560,7 +560,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       uint8_t* sOp = smem + BO_OP + g * (2 * 128 * 128);
       trace_stamp(2 + g, i, 0, f == 0);
       mbar_wait_guard(bar(C_META_FULL + ms), mph);
-      float gm = ldg_byte_off(gmf, (uint32_t)sOwn[0] * (uint32_t)(NF * 4));
+      float gm = __ldg(gmf + (size_t)sOwn[0] * NF);
       // Two half-tiles of 64 edges: all 64 row gathers of a half are in flight at once (the latency of the L2
       // gathers is paid twice per tile instead of once per 16 rows: 8.6k -> ~4k cycles in the timeline trace); the
       // first half is issued before the operand buffer is even free.
@@ -569,8 +569,8 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
           const uint4 m = sMeta2[h * 32 + u];
-          av[2 * u] = ldg_byte_off(af, m.x);
-          av[2 * u + 1] = ldg_byte_off(af, m.z);
+          av[2 * u] = __ldg(af + m.x);      // (ldg_byte_off here costs registers: 64 addresses live at once -> spills)
+          av[2 * u + 1] = __ldg(af + m.z);
         }
       };
       auto emit64 = [&](int h) {
@@ -586,7 +586,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
             } else {
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                if ((bits >> (8 * q + u)) & 1u) gm = ldg_byte_off(gmf, (uint32_t)sOwn[h * 64 + w * 32 + q * 8 + u] * (uint32_t)(NF * 4));
+                if ((bits >> (8 * q + u)) & 1u) gm = __ldg(gmf + (size_t)sOwn[h * 64 + w * 32 + q * 8 + u] * NF);
                 v[u] *= gm;
               }
             }
