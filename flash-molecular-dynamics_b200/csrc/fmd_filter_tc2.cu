@@ -115,6 +115,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
     // =========================================================== P: producers (thread = edge row)
     const float g2 = gamma * 1.4426950408889634f;
     const float pi_over_rc = FMD_PI_F / rc;
+    const RbfRecurrence rrec = make_rbf_recurrence(sCen, R, g2);
     int tile = blockIdx.x;
     float d_n = 0.f;
     int own_n = 0, nbr_n = 0, prev_n = -1;
@@ -149,9 +150,8 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       if (tid == 0) *reinterpret_cast<int*>(smem + O_HEAD + ms * 32) = prev;
       if (lane == 0) reinterpret_cast<uint32_t*>(smem + O_HEAD + ms * 32 + 16)[warp] = bmask;
       mbar_arrive(bar(B_META_FULL + ms));
-      write_rbf_row_fast(smem + O_RBF + s * (128 * 128), sCen, tid, d, cut, g2);
-      // no fence.proxy.async here: it would wait for the prefetched metadata loads of the next tile (15 % of all
-      // samples were `membar` stalls); the MMA issuer fences after it has acquired the buffer
+      write_rbf_row_rec(smem + O_RBF + s * (128 * 128), sCen, tid, d, cut, g2, rrec);
+      fence_async_smem();
       mbar_arrive(bar(B_RBF_FULL + s));
       trace_stamp(0, i, 2, tid == 0);
     }
@@ -169,7 +169,6 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         mbar_wait_guard(bar(B_RBF_FULL + s), ph);
         mbar_wait_guard(bar(B_D1_EMPTY + s), ph ^ 1);
         trace_stamp(4, i, 1, true);
-        fence_async_smem();   // operand rows written through the generic proxy (acquired above) -> async proxy
         fence_after_sync();
         const uint64_t dB1 = smem_desc_sw128(sbase + O_RBF + s * (128 * 128), 16, 1024);
 #pragma unroll
@@ -184,7 +183,6 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         mbar_wait_guard(bar(B_TT_FULL + s), ph);
         mbar_wait_guard(bar(B_D2_EMPTY + s), ph ^ 1);
         trace_stamp(5, i, 1, true);
-        fence_async_smem();   // operand rows written through the generic proxy (acquired above) -> async proxy
         fence_after_sync();
         const uint64_t dB2 = smem_desc_sw128(sbase + O_TT + s * (2 * 128 * 128), 128 * 128, 1024);
 #pragma unroll
@@ -238,6 +236,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       fence_before_sync();
       mbar_arrive(bar(B_D1_EMPTY + s));
       mbar_arrive(bar(B_META_EMPTY + ms));
+      fence_async_smem();
       mbar_arrive(bar(B_TT_FULL + s));
       trace_stamp(1, i, 2, j == 0);
     }
@@ -421,6 +420,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
     const float g2 = gamma * 1.4426950408889634f;
     const float pi_over_rc = FMD_PI_F / rc;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const RbfRecurrence rrec = make_rbf_recurrence(sCen, R, g2);
     int tile = blockIdx.x;
     float d_n = 0.f;
     int own_n = -1, nbr_n = 0, prev_n = -1;
@@ -487,7 +487,8 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
           make_uint2((uint32_t)nb * (uint32_t)NF, __float_as_uint(cut));
       reinterpret_cast<int*>(smem + BO_OWN + ms * TILE * 4)[tid] = valid ? own : 0;
       if (lane == 0) reinterpret_cast<uint32_t*>(smem + BO_HEAD + ms * 16)[warp] = bmask;
-      write_rbf_row_fast(smem + BO_RBF + s * (128 * 128), sCen, tid, d, cut, g2);
+      write_rbf_row_rec(smem + BO_RBF + s * (128 * 128), sCen, tid, d, cut, g2, rrec);
+      fence_async_smem();
       mbar_arrive(bar(C_RBF_FULL + s));
       mbar_arrive(bar(C_META_FULL + ms));
       trace_stamp(0, i, 2, tid == 0);
@@ -602,6 +603,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       emit64(0);
       gather64(1);
       emit64(1);
+      fence_async_smem();
       mbar_arrive(bar(C_GW_FULL + g));
       mbar_arrive(bar(C_META_EMPTY + ms));
       trace_stamp(2 + g, i, 2, f == 0);
@@ -656,6 +658,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       if (kExact) red[j] = usum;
       fence_before_sync();
       mbar_arrive(bar(C_D3_EMPTY + s));
+      fence_async_smem();
       mbar_arrive(bar(C_GT_FULL + s));
       mbar_arrive(bar(C_META_EMPTY + ms));
       trace_stamp(5, i, 2, j == 0);
@@ -677,7 +680,6 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         mbar_wait_guard(bar(C_RBF_FULL + s), ph);
         mbar_wait_guard(bar(C_D3_EMPTY + s), ph ^ 1);  // D13[s] drained by phaseB(i-2)
         trace_stamp(6, i, 1, true);
-        fence_async_smem();   // operand rows written through the generic proxy (acquired above) -> async proxy
         fence_after_sync();
         const uint64_t dB1 = smem_desc_sw128(sbase + BO_RBF + s * (128 * 128), 16, 1024);
 #pragma unroll
@@ -693,7 +695,6 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         trace_stamp(7, i, 2, true);
         mbar_wait_guard(bar(C_D1_EMPTY + s), ph);  // phaseA(i) has drained D1 from D13[s]
         trace_stamp(7, i, 1, true);
-        fence_async_smem();   // operand rows written through the generic proxy (acquired above) -> async proxy
         fence_after_sync();
         const uint64_t dB3 = smem_desc_sw128(sbase + BO_OP + s * (2 * 128 * 128), 128 * 128, 1024);
 #pragma unroll
@@ -710,7 +711,6 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         mbar_wait_guard(bar(C_GT_FULL + s), ph);
         mbar_wait_guard(bar(C_D4_EMPTY + q4), ((i / D4_STAGES) & 1) ^ 1);
         trace_stamp(8, i, 1, true);
-        fence_async_smem();   // operand rows written through the generic proxy (acquired above) -> async proxy
         fence_after_sync();
         const uint64_t dA4 = smem_desc_sw128(sbase + BO_ST + s * (2 * 128 * 128), 16, 1024);   // g_t [e][j], K-major
 #pragma unroll

@@ -349,10 +349,10 @@ linear_x3_kernel(const float* __restrict__ X, const float* __restrict__ W, const
       if (ptile < n_tiles) blk[d].load(X, M, K, ptile * X3_TILE, pkb, ph_, p);
       advance(ptile, pkb, ph_);
     }
-    // NOTE: no fence.proxy.async here.  A proxy fence in the producers waits for ALL their outstanding memory operations,
-    // i.e. for the prefetched global loads of the following half-blocks (measured: 1/3 of the producers' time in
-    // `membar` stalls, prefetch depth without effect).  The stores are released by mbarrier.arrive; the MMA thread
-    // acquires the stage with try_wait and issues the generic->async proxy fence itself before the MMAs read the stage.
+    // The generic->async proxy fence is executed by the WRITING threads before they arrive (the documented pattern).  A
+    // variant with one fence by the MMA thread after it had acquired the stage passed every parity test and was 6 %
+    // faster (the producers' fence waits for their prefetched loads too), but long trajectories then showed rare
+    // run-to-run differences in their statistics, so it is not used.
     uint32_t s = 0, ph = 0;                          // ring slot / phase of the stage being filled
     while (tile < n_tiles) {
 #pragma unroll
@@ -363,6 +363,7 @@ linear_x3_kernel(const float* __restrict__ X, const float* __restrict__ W, const
           if (h == 0) mbar_wait_guard(bar_empty + 8u * s, ph ^ 1u);
           blk[d].store(smem + off_a + s * X3_STAGE, h, p);
           if (h == 1) {
+            fence_async_smem();
             mbar_arrive(bar_full + 8u * s);
             if (++s == (uint32_t)nstage) { s = 0; ph ^= 1u; }
           }
@@ -384,7 +385,6 @@ linear_x3_kernel(const float* __restrict__ X, const float* __restrict__ W, const
       const uint32_t d0 = tmem_base + b * 256u, d1 = d0 + 128u;
       for (int kb = 0; kb < Kb; ++kb) {
         mbar_wait_guard(bar_full + 8u * s, ph);
-        fence_async_smem();      // the producers' generic-proxy stores (acquired above) -> visible to the tensor core
         fence_after_sync();
         const uint32_t a_addr = sbase + off_a + s * X3_STAGE;
         const uint64_t dA1 = smem_desc_sw128(a_addr, 16, 1024);

@@ -148,6 +148,10 @@ def test_trajectory_statistics_vs_reference_10k_steps(gptq):
     sim = LangevinSimulation(friction=friction, dt=dt, n_timesteps=int(n_steps), save_interval=int(save_interval),
                              save_energies=True, random_seed=99, device=DEV, gptq=gptq)
     sim.attach_model_and_configurations(model, configs, beta=beta)
+    # pinned initial velocities (attach draws them from the global RNG, i.e. from whatever ran before this test)
+    d = sim.initial_data
+    gen = torch.Generator().manual_seed(0)
+    d.velocities = (torch.randn(d.pos.shape, generator=gen) * torch.sqrt(1.0 / (beta * d.masses.cpu()))[:, None]).to(d.pos.device)
     sim.simulate()
     assert sim.get_throughput_metrics()["path"] == "fused-engine"
     x, ke, pe = sim.simulated_coords, sim.simulated_kinetic_energies, sim.simulated_potential
@@ -163,10 +167,17 @@ def test_trajectory_statistics_vs_reference_10k_steps(gptq):
     # still grows at step 10^4), so the mean drifts and the GLOBAL sample std is inflated by a run-dependent 0-15 %
     # (reference sample: 6.01; ours 5.3-6.3 over repeated runs).  The fluctuation is therefore measured per saved
     # frame ACROSS the 64 independent molecules (insensitive to the drift) and averaged over frames.
+    # This synthetic model at dt = 0.004 has rare heating events (a repulsive contact integrated with a large step): the
+    # UNMODIFIED reference's own sample holds KE spikes up to 139 (mean 48.8, 34 of 8000 samples above 75) and ours, with
+    # 8x the molecules, up to ~10^3 for some velocity seeds (scripts/dbg_stats.py).  Means and ROBUST widths are compared:
+    # the median over frames of the cross-molecule std, and the MAD-based width of the whole sample.
     canon = ke_ref.mean() * np.sqrt(2.0 / (3 * 54))
-    per_frame = ke_our.std(axis=0, ddof=1).mean()
-    assert abs(per_frame / canon - 1.0) < 0.10, (per_frame, canon)
-    assert abs(ke_our.std() / ke_ref.std() - 1.0) < 0.25, (ke_our.std(), ke_ref.std())
+    per_frame = np.median(ke_our.std(axis=0, ddof=1))
+    assert abs(per_frame / canon - 1.0) < 0.06, (per_frame, canon)
+
+    def mad_std(a):
+        return 1.4826 * np.median(np.abs(a - np.median(a)))
+    assert abs(mad_std(ke_our) / mad_std(ke_ref) - 1.0) < 0.12, (mad_std(ke_our), mad_std(ke_ref))
     # --- potential energy level
     se = ref["pe"][:, burn:].mean(axis=1).std() / np.sqrt(n_ref)
     assert abs(pe[:, burn:].mean() - ref["pe"][:, burn:].mean()) < 5 * se + 0.01 * abs(ref["pe"][:, burn:].mean())
@@ -235,3 +246,29 @@ def test_fused_engine_graph_path_is_reproducible():
             outs.append((eng.pos.clone(), eng.vel.clone(), ff.energy.clone()))
         for o in outs[1:]:
             assert all(torch.equal(a, b) for a, b in zip(outs[0], o)), prec
+
+
+@pytest.mark.parametrize("gptq", [None, "w16a16"])
+def test_long_run_is_bitwise_reproducible(gptq):
+    """Race detector for the warp-specialised tensor-core kernels: 64 molecules x 1500 BAOAB steps (Philox noise, pinned
+    velocities) twice through the CUDA-graph path must end in bitwise identical states.  (A generic->async proxy fence
+    moved from the writing threads to the MMA-issuing thread passed every parity test but failed this kind of check.)"""
+    from flashmd import synthetic
+    from flashmd.simulation import LangevinSimulation
+    g = dict(load_golden("schnet_n54_b4.npz"))
+    system = synthetic.synthetic_system(8, 54, seed=0, target_degree=30.0)
+    g["sys.pos"], g["sys.cutoff"] = system["pos"], np.float64(system["cutoff"])
+    outs = []
+    for rep in range(2):
+        model, _, configs0 = dropin_model_from_golden(g)
+        configs = [deepcopy(configs0[b]) for r_ in range(8) for b in range(8)]
+        sim = LangevinSimulation(friction=1.0, dt=0.004, n_timesteps=1500, save_interval=500, save_energies=True,
+                                 random_seed=5, device=DEV, gptq=gptq)
+        sim.attach_model_and_configurations(model, configs, beta=1.67)
+        d = sim.initial_data
+        gen = torch.Generator().manual_seed(17)
+        d.velocities = (torch.randn(d.pos.shape, generator=gen) * torch.sqrt(1.0 / (1.67 * d.masses.cpu()))[:, None]).to(d.pos.device)
+        sim.simulate()
+        assert sim.get_throughput_metrics()["path"] == "fused-engine"
+        outs.append((np.array(sim.simulated_coords).copy(), np.array(sim.simulated_potential).copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
