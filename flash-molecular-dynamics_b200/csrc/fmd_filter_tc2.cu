@@ -31,10 +31,11 @@ __device__ __forceinline__ void trace_stamp(int role, int tile, int k, bool lead
 // `base + element_offset` was IADD3 + IMAD.X + LEA + LEA.HI.X per element, 4 of the 5 instructions of every gathered
 // element and 20 % of all instructions of the forward kernel)
 __device__ __forceinline__ float ldg_byte_off(const float* base, uint32_t byte_off) {
-  uint64_t addr;
-  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(byte_off), "l"(base));
   float v;
-  asm("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+  // address formation and load in ONE asm block: the 64-bit address is a transient register (with a separate mad.wide
+  // the compiler hoisted all 64 addresses of a gather batch ahead of the loads and spilled)
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 1, %2;\n\tld.global.nc.f32 %0, [a];\n\t}"
+               : "=f"(v) : "r"(byte_off), "l"(base));
   return v;
 }
 
@@ -145,7 +146,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_wait_guard(bar(B_RBF_EMPTY + s), ph ^ 1);
       trace_stamp(0, i, 1, tid == 0);
       reinterpret_cast<uint32_t*>(smem + O_XOFF + ms * TILE * 4)[tid] = (uint32_t)nb * (uint32_t)(NF * 4);
-      reinterpret_cast<float*>(smem + O_CUT + ms * TILE * 4)[tid] = cut;
+      reinterpret_cast<__half*>(smem + O_CUT + ms * TILE * 4)[tid] = __float2half_rn(cut);   // fp16: consumed as half2 pairs
       reinterpret_cast<int*>(smem + O_OWN + ms * TILE * 4)[tid] = own;
       if (tid == 0) *reinterpret_cast<int*>(smem + O_HEAD + ms * 32) = prev;
       if (lane == 0) reinterpret_cast<uint32_t*>(smem + O_HEAD + ms * 32 + 16)[warp] = bmask;
@@ -212,7 +213,7 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       trace_stamp(1, i, 1, j == 0);
       fence_after_sync();
       uint8_t* sTT = smem + O_TT + s * (2 * 128 * 128);
-      const float4* sCut4 = reinterpret_cast<const float4*>(smem + O_CUT + ms * TILE * 4);
+      const uint4* sCutH = reinterpret_cast<const uint4*>(smem + O_CUT + ms * TILE * 4);   // 8 fp16 cut-offs per load
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
@@ -220,14 +221,15 @@ filter_cfconv_fwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          // t * C(d_e): D2 is linear in t, so the cut-off rides through the second GEMM for free
-          const float4 ca = sCut4[c * 8 + q * 2], cb = sCut4[c * 8 + q * 2 + 1];
-          const float cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+          // t * C(d_e): D2 is linear in t, so the cut-off rides through the second GEMM for free.  tanh on packed fp16
+          // pairs: one MUFU operation and one HMUL2 per two values (the result is an fp16 operand anyway)
+          const uint4 cq = sCutH[c * 4 + q];
+          const uint32_t cc[4] = {cq.x, cq.y, cq.z, cq.w};
           uint32_t p[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            p[u] = pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u]) + bias) * cc[2 * u],
-                              tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]) + bias) * cc[2 * u + 1]);
+            p[u] = hmul2_u32(tanh_approx_h2(pack_half2(__uint_as_float(r[q * 8 + 2 * u]) + bias,
+                                                       __uint_as_float(r[q * 8 + 2 * u + 1]) + bias)), cc[u]);
           const int chunk = c * 4 + q;
           *reinterpret_cast<uint4*>(sTT + (chunk >> 3) * (128 * 128) + sw128_off(j, chunk & 7)) =
               make_uint4(p[0], p[1], p[2], p[3]);
@@ -484,7 +486,7 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
       mbar_wait_guard(bar(C_RBF_EMPTY + s), ph ^ 1);
       trace_stamp(0, i, 1, tid == 0);
       reinterpret_cast<uint2*>(smem + BO_META + ms * TILE * 8)[tid] =
-          make_uint2((uint32_t)nb * (uint32_t)NF, __float_as_uint(cut));
+          make_uint2((uint32_t)nb * (uint32_t)(NF * 4), __float_as_uint(cut));   // byte offset of the gathered row
       reinterpret_cast<int*>(smem + BO_OWN + ms * TILE * 4)[tid] = valid ? own : 0;
       if (lane == 0) reinterpret_cast<uint32_t*>(smem + BO_HEAD + ms * 16)[warp] = bmask;
       write_rbf_row_rec(smem + BO_RBF + s * (128 * 128), sCen, tid, d, cut, g2, rrec);
@@ -540,8 +542,8 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
           uint32_t p[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            p[u] = pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u]) + bj[2 * u]),
-                              tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]) + bj[2 * u + 1]));
+            p[u] = tanh_approx_h2(pack_half2(__uint_as_float(r[q * 8 + 2 * u]) + bj[2 * u],
+                                             __uint_as_float(r[q * 8 + 2 * u + 1]) + bj[2 * u + 1]));
           const int chunk = c * 4 + q;   // 8 consecutive features j of edge row f (= this thread's edge)
           *reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + sw128_off(f, chunk & 7)) =
               make_uint4(p[0], p[1], p[2], p[3]);
@@ -570,8 +572,8 @@ filter_cfconv_bwd2_kernel(const float* __restrict__ dist, const int32_t* __restr
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
           const uint4 m = sMeta2[h * 32 + u];
-          av[2 * u] = __ldg(af + m.x);      // (ldg_byte_off here costs registers: 64 addresses live at once -> spills)
-          av[2 * u + 1] = __ldg(af + m.z);
+          av[2 * u] = ldg_byte_off(af, m.x);
+          av[2 * u + 1] = ldg_byte_off(af, m.z);
         }
       };
       auto emit64 = [&](int h) {

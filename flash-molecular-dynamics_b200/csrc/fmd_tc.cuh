@@ -137,6 +137,17 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// two tanh values per MUFU operation, fp16 in / fp16 out (abs error ~2^-11, the rounding level of the fp16 operand)
+__device__ __forceinline__ uint32_t tanh_approx_h2(uint32_t x) {
+  uint32_t y;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+  return y;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
