@@ -344,13 +344,18 @@ class _Simulation:
         pass
 
     def get_throughput_metrics(self) -> dict:
-        """timestep*mol/s over the second half of the run (reference base.py:748-787)."""
+        """timestep*mol/s over the second half of the run: the reference's keys (base.py:748-787: second_half_elapsed_time,
+        second_half_steps, throughput, ms_per_timestep, first_half_steps, n_sims, n_atoms, peak_memory_*_gb; None before a
+        run) plus `path` (fused-engine | module) and the earlier names of this package as aliases."""
         if self._warmup_end_time is None or self._simulation_end_time is None:
-            return {}
+            return None
         dt = self._simulation_end_time - self._warmup_end_time
-        return {"post_warmup_steps": self._post_warmup_steps, "post_warmup_time_s": dt, "n_sims": self.n_sims,
-                "throughput_timestep_mol_per_s": self._post_warmup_steps * self.n_sims / max(dt, 1e-12),
-                "ms_per_step": 1e3 * dt / max(self._post_warmup_steps, 1),
+        steps = self._post_warmup_steps
+        thr = steps * self.n_sims / dt if (dt > 0 and steps > 0) else 0
+        ms = 1e3 * dt / steps if (dt > 0 and steps > 0) else 0
+        return {"second_half_elapsed_time": dt, "second_half_steps": steps, "throughput": thr, "ms_per_timestep": ms,
+                "first_half_steps": self.n_timesteps // 2, "n_sims": self.n_sims, "n_atoms": self.n_atoms,
                 "peak_memory_allocated_gb": self._second_half_peak_memory_allocated,
                 "peak_memory_reserved_gb": self._second_half_peak_memory_reserved,
-                "path": "fused-engine" if self.engine is not None else "module"}
+                "path": "fused-engine" if self.engine is not None else "module",
+                "post_warmup_steps": steps, "post_warmup_time_s": dt, "throughput_timestep_mol_per_s": thr, "ms_per_step": ms}
