@@ -22,6 +22,52 @@ from ..data._keys import ENERGY_KEY, FORCE_KEY, MASS_KEY, POSITIONS_KEY, VELOCIT
 from .specialize_prior import condense_all_priors_for_simulation
 
 
+class _AsyncSaver:
+    """Save points of the fused path without stalling the graphed step: the tensors of a save
+    point are snapshotted on the compute stream (device-to-device, in order), copied to pinned host memory on a side
+    stream, and consumed (stored into the trajectory buffers, blow-up / capacity checks) when their slot comes round again,
+    at the next export, or at the end of the run.  `n_slots` save points may be in flight."""
+
+    def __init__(self, device, n_slots: int = 3):
+        self.device = device
+        self.stream = torch.cuda.Stream(device)
+        self.n_slots = n_slots
+        self.pending = []          # FIFO of (done_event, host_tensors, device_snapshots, callback)
+        self.pinned = [dict() for _ in range(n_slots)]
+        self.k = 0
+
+    def submit(self, tensors, callback):
+        while len(self.pending) >= self.n_slots:
+            self._finish_one()
+        slot = self.k % self.n_slots
+        self.k += 1
+        snaps = {k: v.detach().clone() for k, v in tensors.items()}     # ordered after the step on the compute stream
+        ready = torch.cuda.Event()
+        ready.record()
+        host = {}
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            for k, v in snaps.items():
+                buf = self.pinned[slot].get(k)
+                if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                    buf = self.pinned[slot][k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                buf.copy_(v, non_blocking=True)
+                host[k] = buf
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.pending.append((done, host, snaps, callback))
+
+    def _finish_one(self):
+        done, host, snaps, callback = self.pending.pop(0)
+        done.synchronize()
+        del snaps
+        callback(host)
+
+    def drain(self):
+        while self.pending:
+            self._finish_one()
+
+
 class _Simulation:
     def __init__(self, dt: float = 5e-4, save_forces: bool = False, save_energies: bool = False,
                  save_force_components: bool = False, save_energy_components: bool = False,
@@ -79,6 +125,7 @@ class _Simulation:
         self.checkpointed_data = None
         self.engine = None
         self._warmup_end_time = self._simulation_end_time = None
+        self._saver = None
         self._post_warmup_steps = 0
 
     # ------------------------------------------------------------------ option checks
@@ -205,12 +252,58 @@ class _Simulation:
     def _swap_and_export(t: torch.Tensor) -> np.ndarray:
         return t.detach().cpu().numpy().swapaxes(0, 1)
 
+    def _extra_save_tensors(self) -> dict:
+        """Subclasses: further device tensors of a save point on the fused path (name -> tensor)."""
+        return {}
+
+    def _store_extra(self, i: int, host: dict, bufs: dict):
+        pass
+
+    def _traj_buffers(self) -> dict:
+        return {"coords": self.simulated_coords, "forces": self.simulated_forces, "potential": self.simulated_potential}
+
     def save(self, pos, vel, forces, potential, t: int):
+        i = t // self.save_interval - self._npy_file_index * self._save_size
         x = pos.view(-1, self.n_atoms, self.n_dims)
         spread = x.std(dim=(1, 2))
+        if self.engine is not None:
+            # fused path: nothing here waits for the GPU
+            eng = self.engine
+            status = torch.stack([spread.max(), torch.isnan(spread).any().float(),
+                                  eng.ff.n_edges_dev[0].float() if eng.ff.w is not None else spread.new_zeros(())])
+            tensors = {"pos": x, "status": status}
+            if self.save_forces:
+                tensors["forces"] = forces.view(-1, self.n_atoms, self.n_dims)
+            if self.save_energies:
+                tensors["potential"] = potential
+            if self.create_checkpoints:
+                tensors["vel"] = vel
+            tensors.update(self._extra_save_tensors())
+            bufs = self._traj_buffers()
+            limit = 1e3 * float(self.initial_pos_spread)
+            cap = eng.ff.cap if eng.ff.w is not None else None
+
+            def done(host, i=i, t=t, bufs=bufs):
+                smax, snan, n_edges = (float(v) for v in host["status"])
+                if snan > 0 or not (smax <= limit):
+                    raise RuntimeError(f"Simulation of trajectory blew up at #timestep={t}")
+                if cap is not None and n_edges > cap:
+                    raise RuntimeError(f"neighbour list overflow at #timestep={t}: {int(n_edges)} edges > capacity {cap}")
+                bufs["coords"][i] = host["pos"]
+                if self.save_forces:
+                    bufs["forces"][i] = host["forces"]
+                if self.save_energies:
+                    bufs["potential"][i] = host["potential"]
+                if self.create_checkpoints:
+                    self.checkpoint = {POSITIONS_KEY: host["pos"].reshape(-1, self.n_dims).clone(),
+                                       VELOCITY_KEY: host["vel"].clone()}
+                self._store_extra(i, host, bufs)
+            if self._saver is None:
+                self._saver = _AsyncSaver(self.device)
+            self._saver.submit(tensors, done)
+            return i
         if bool(((spread.max() > 1e3 * self.initial_pos_spread.to(spread.device)) | torch.isnan(spread).any()).item()):
             raise RuntimeError(f"Simulation of trajectory blew up at #timestep={t}")
-        i = t // self.save_interval - self._npy_file_index * self._save_size
         self.simulated_coords[i] = x.cpu()
         if self.save_forces:
             self.simulated_forces[i] = forces.view(-1, self.n_atoms, self.n_dims).cpu()
@@ -221,6 +314,8 @@ class _Simulation:
         return i
 
     def write(self):
+        if self._saver is not None:
+            self._saver.drain()            # every save point of this export interval has reached the host buffers
         key = self._get_numpy_count()
         np.save(f"{self.filename}_coords_{key}.npy", self._swap_and_export(self.simulated_coords))
         if self.save_forces:
@@ -283,10 +378,7 @@ class _Simulation:
                 data, potential, forces = self.timestep(data, forces)
                 pos, vel = data[POSITIONS_KEY], data[VELOCITY_KEY] if VELOCITY_KEY in data else None
             if (t + 1) % self.save_interval == 0:
-                if eng is not None and eng.ff.w is not None and eng.ff.num_edges() > eng.ff.cap:
-                    raise RuntimeError(f"neighbour list overflow at #timestep={t}: {eng.ff.num_edges()} edges > "
-                                       f"capacity {eng.ff.cap}")
-                self.save(pos, vel, forces, potential, t)
+                self.save(pos, vel, forces, potential, t)   # fused path: asynchronous (incl. the capacity check)
                 if self.export_interval is not None and (t + 1) % self.export_interval == 0:
                     self.write()
                     if self.save_subroutine is not None:
@@ -306,6 +398,8 @@ class _Simulation:
                 prof.step()
             if self.profile_end_step is not None and t == self.profile_end_step and cuda:
                 torch.cuda.cudart().cudaProfilerStop()
+        if self._saver is not None:
+            self._saver.drain()
         if cuda:
             torch.cuda.synchronize()
         self._simulation_end_time = time.perf_counter()

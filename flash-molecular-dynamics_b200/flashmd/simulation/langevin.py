@@ -82,18 +82,29 @@ class LangevinSimulation(_Simulation):
         eng.step()
 
     # ------------------------------------------------------------------ output
+    def _extra_save_tensors(self) -> dict:
+        return {"ke": self.engine.ke} if self.save_energies else {}
+
+    def _traj_buffers(self) -> dict:
+        b = super()._traj_buffers()
+        b["ke"] = self.simulated_kinetic_energies
+        return b
+
+    def _store_extra(self, i: int, host: dict, bufs: dict):
+        if self.save_energies:
+            bufs["ke"][i] = host["ke"]
+
     def save(self, pos, vel, forces, potential, t: int):
         i = super().save(pos, vel, forces, potential, t)
-        if self.save_energies:
-            if self.engine is not None:
-                ke = self.engine.ke
-            else:
-                m = self.initial_data[MASS_KEY].view(self.n_sims, self.n_atoms)
-                ke = 0.5 * (m[:, :, None] * vel.view(-1, self.n_atoms, self.n_dims) ** 2).sum(dim=(1, 2))
+        if self.save_energies and self.engine is None:      # module path (the fused path stores KE asynchronously)
+            m = self.initial_data[MASS_KEY].view(self.n_sims, self.n_atoms)
+            ke = 0.5 * (m[:, :, None] * vel.view(-1, self.n_atoms, self.n_dims) ** 2).sum(dim=(1, 2))
             self.simulated_kinetic_energies[i] = ke.cpu()
         return i
 
     def write(self):
+        if self._saver is not None:
+            self._saver.drain()
         if self.save_energies:
             np.save(f"{self.filename}_kineticenergy_{self._get_numpy_count()}.npy",
                     self._swap_and_export(self.simulated_kinetic_energies))

@@ -272,3 +272,29 @@ def test_long_run_is_bitwise_reproducible(gptq):
         assert sim.get_throughput_metrics()["path"] == "fused-engine"
         outs.append((np.array(sim.simulated_coords).copy(), np.array(sim.simulated_potential).copy()))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_async_save_points_are_consistent_snapshots():
+    """Save points of the fused path are copied to the host asynchronously (device snapshot -> pinned staging on a side
+    stream) while the next steps already run: saving EVERY step must give the same frames as saving every 5th step, and
+    forces / energies / kinetic energies must belong to the same step as the coordinates."""
+    from flashmd.simulation import LangevinSimulation
+    g = load_golden("schnet_n54_b4.npz")
+    runs = {}
+    for si in (1, 5):
+        model, _, configs = dropin_model_from_golden(g)
+        sim = LangevinSimulation(friction=1.0, dt=0.004, n_timesteps=60, save_interval=si, export_interval=None,
+                                 save_forces=True, save_energies=True, random_seed=21, device=DEV, gptq="w16a16")
+        sim.attach_model_and_configurations(model, configs, beta=1.67)
+        d = sim.initial_data
+        gen = torch.Generator().manual_seed(1)
+        d.velocities = (torch.randn(d.pos.shape, generator=gen) * torch.sqrt(1.0 / (1.67 * d.masses.cpu()))[:, None]).to(d.pos.device)
+        sim.simulate()
+        assert sim.get_throughput_metrics()["path"] == "fused-engine"
+        runs[si] = (np.array(sim.simulated_coords), np.array(sim.simulated_forces), np.array(sim.simulated_potential),
+                    np.array(sim.simulated_kinetic_energies))
+    for a, b in zip(runs[1], runs[5]):
+        assert a.shape[1] == 60 and b.shape[1] == 12
+        assert np.array_equal(a[:, 4::5], b)
+    # consecutive frames differ (the snapshots are not all the same late state)
+    assert np.abs(np.diff(runs[1][0], axis=1)).max(axis=(0, 2, 3)).min() > 0
