@@ -415,8 +415,8 @@ def test_schnet_w16a16(name):
     assert rel_l2(f.cpu(), g["ref64.forces.SchNet"]) < 2e-2
 
 
-@pytest.mark.parametrize("exact", [True, False])
-def test_fused_tensor_core_path_vs_materialised_path(exact):
+@pytest.mark.parametrize("exact,uniform_centres", [(True, True), (False, True), (True, False)])
+def test_fused_tensor_core_path_vs_materialised_path(exact, uniform_centres):
     """The tcgen05 fused filter-network x CFConv kernels (no [E,F] tensor in HBM) against the materialised
     SIMT W16A16 pipeline on the same inputs: same rounding model up to tanh.approx / fp32-kept W, far
     inside the 1e-2 bar; run-to-run bit-identical (no atomics)."""
@@ -428,6 +428,11 @@ def test_fused_tensor_core_path_vs_materialised_path(exact):
     types = torch.from_numpy(sysd["atom_types"]).repeat(B).to(DEV)
     ptr = (torch.arange(B + 1) * n).to(DEV)
     w = SchNetWeights.from_flat(random_schnet_tensors(5), sysd["cutoff"], 50, DEV)
+    if not uniform_centres:
+        # a trained basis: unequally spaced centres -> the fused kernels must leave the multiplicative recurrence of the
+        # radial basis rows (valid for linspace centres only) for the direct evaluation
+        gen = torch.Generator().manual_seed(2)
+        w.centers = (w.centers.cpu() + 0.3 * float(w.centers[1] - w.centers[0]) * (torch.rand(50, generator=gen) - 0.5)).to(DEV)
     ff_tc = ForceField(w, [], types, ptr, precision="w16a16", exact_cutoff_grad=exact)
     ff_mat = ForceField(w, [], types, ptr, precision="w16a16", exact_cutoff_grad=exact, use_tensor_cores=False)
     assert ff_tc.fused_tc and not ff_mat.fused_tc
