@@ -32,9 +32,14 @@ __device__ __forceinline__ V3 cross(V3 a, V3 b) {
 
 constexpr int WARPS = 8;
 
+// PACKED: two-body records are 8 bytes {other | kind << 28, parameter id} and the parameters (k, x0, V0 | sigma) come
+// from a small deduplicated float4 table (a few hundred type pairs: L1-resident) - the 16-byte records were 147 MB of
+// HBM traffic per step at 128 x 269 beads, by far the largest stream outside the two fused edge kernels.
+template <bool PACKED>
 __global__ void __launch_bounds__(WARPS * 32)
 prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __restrict__ pair_ptr,
-                 const int4* __restrict__ pair_ent, const int32_t* __restrict__ mb_ptr,
+                 const void* __restrict__ pair_ent_v, const float4* __restrict__ pair_tab,
+                 const int32_t* __restrict__ mb_ptr,
                  const int32_t* __restrict__ mb_ent, const int32_t* __restrict__ ang_map, int n_ang,
                  const float* __restrict__ ang_k, const float* __restrict__ ang_x0, const float* __restrict__ ang_v0,
                  const int32_t* __restrict__ dih_map, int n_dih, const float* __restrict__ dih_k1,
@@ -49,11 +54,19 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
   // ---- two-body terms: entry = {other | kind << 28, p0, p1, p2}
   if (pair_ptr) {
     const int p1 = __ldg(&pair_ptr[a + 1]);
-#pragma unroll 4   // independent record -> position load chains in flight (the loop is latency-bound)
+#pragma unroll 8   // independent record -> position load chains in flight (the loop is latency-bound on the record stream)
     for (int p = __ldg(&pair_ptr[a]) + lane; p < p1; p += 32) {
-      const int4 ent = __ldg(&pair_ent[p]);
-      const int other = ent.x & 0x0FFFFFFF, kind = ent.x >> 28;
-      const float q0 = __int_as_float(ent.y), q1 = __int_as_float(ent.z), q2 = __int_as_float(ent.w);
+      int head;
+      float q0, q1, q2;
+      if (PACKED) {
+        const int2 ent = __ldg(reinterpret_cast<const int2*>(pair_ent_v) + p);
+        const float4 q = __ldg(&pair_tab[ent.y]);
+        head = ent.x; q0 = q.x; q1 = q.y; q2 = q.z;
+      } else {
+        const int4 ent = __ldg(reinterpret_cast<const int4*>(pair_ent_v) + p);
+        head = ent.x; q0 = __int_as_float(ent.y); q1 = __int_as_float(ent.z); q2 = __int_as_float(ent.w);
+      }
+      const int other = head & 0x0FFFFFFF, kind = head >> 28;
       const V3 dr = sub(ld3(pos, other), pa);
       const float d = sqrtf(dot(dr, dr));
       float et, dEdd;
@@ -141,7 +154,7 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
 }  // namespace
 
 extern "C" int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair_ptr, const void* pair_ent,
-                              const int32_t* mb_ptr, const int32_t* mb_ent, const int32_t* ang_map, int n_ang,
+                              const float* pair_tab, const int32_t* mb_ptr, const int32_t* mb_ent, const int32_t* ang_map, int n_ang,
                               const float* ang_k, const float* ang_x0, const float* ang_v0, const int32_t* dih_map,
                               int n_dih, const float* dih_k1, const float* dih_k2, const float* dih_v0, int n_degs,
                               float* e_atom, float* forces, int accumulate_forces, void* stream) {
@@ -151,9 +164,15 @@ extern "C" int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair
   FMD_REQUIRE(n_ang == 0 || (ang_map && ang_k && ang_x0), "fmd_priors_csr: missing angle tables");
   FMD_REQUIRE(n_dih == 0 || (dih_map && dih_k1 && dih_k2), "fmd_priors_csr: missing dihedral tables");
   if (n_nodes <= 0) return FMD_OK;
-  prior_csr_kernel<<<fmd_div_up(n_nodes, WARPS), WARPS * 32, 0, (cudaStream_t)stream>>>(
-      pos, n_nodes, pair_ptr, (const int4*)pair_ent, mb_ptr, mb_ent, ang_map, n_ang, ang_k, ang_x0, ang_v0, dih_map,
-      n_dih, dih_k1, dih_k2, dih_v0, n_degs, e_atom, forces, accumulate_forces);
+  const int grid = fmd_div_up(n_nodes, WARPS);
+  if (pair_tab)
+    prior_csr_kernel<true><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
+        pos, n_nodes, pair_ptr, pair_ent, (const float4*)pair_tab, mb_ptr, mb_ent, ang_map, n_ang, ang_k, ang_x0, ang_v0,
+        dih_map, n_dih, dih_k1, dih_k2, dih_v0, n_degs, e_atom, forces, accumulate_forces);
+  else
+    prior_csr_kernel<false><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
+        pos, n_nodes, pair_ptr, pair_ent, nullptr, mb_ptr, mb_ent, ang_map, n_ang, ang_k, ang_x0, ang_v0,
+        dih_map, n_dih, dih_k1, dih_k2, dih_v0, n_degs, e_atom, forces, accumulate_forces);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

@@ -80,7 +80,7 @@ _SIGS = {
     "fmd_segment_sum": ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
     "fmd_prior_energy_forces": ([c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p], c_int),
-    "fmd_priors_csr": ([c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+    "fmd_priors_csr": ([c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                         c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                         c_void_p], c_int),
     "fmd_baoab_pre": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p,

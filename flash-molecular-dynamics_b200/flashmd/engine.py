@@ -138,11 +138,19 @@ class PriorCSR:
                 own.append(a)
                 rec.append(torch.stack([(b | (p.kind << 28)).to(i32), p.p0.float().view(i32), q1.float().view(i32),
                                         q2.float().view(i32)], 1))
-        self.pair_ptr = self.pair_ent = None
+        self.pair_ptr = self.pair_ent = self.pair_tab = None
         if own:
             own, rec = torch.cat(own), torch.cat(rec)
             order = torch.argsort(own, stable=True)
-            self.pair_ent = rec[order].contiguous()
+            rec = rec[order].contiguous()
+            # 8-byte records + deduplicated parameter table (a few hundred distinct (kind, k, x0, V0 | sigma) tuples)
+            key = torch.cat([(rec[:, :1] >> 28), rec[:, 1:]], 1)
+            uniq, inv = torch.unique(key, dim=0, return_inverse=True)
+            if uniq.shape[0] <= 65536:
+                self.pair_tab = torch.cat([uniq[:, 1:], torch.zeros_like(uniq[:, :1])], 1).contiguous().view(torch.float32)
+                self.pair_ent = torch.stack([rec[:, 0], inv.to(i32)], 1).contiguous()
+            else:
+                self.pair_ent = rec
             self.pair_ptr = self._ptr(own, n_nodes)
         own, ent = [], []
         for isd, group in ((0, ang), (1, dih)):
@@ -171,7 +179,8 @@ class PriorCSR:
 
     def launch(self, pos, forces, accumulate, st):
         a, d = self.ang, self.dih
-        L.call("fmd_priors_csr", L.ptr(pos), self.n_nodes, L.ptr(self.pair_ptr), L.ptr(self.pair_ent), L.ptr(self.mb_ptr),
+        L.call("fmd_priors_csr", L.ptr(pos), self.n_nodes, L.ptr(self.pair_ptr), L.ptr(self.pair_ent), L.ptr(self.pair_tab),
+               L.ptr(self.mb_ptr),
                L.ptr(self.mb_ent), L.ptr(a.mapping) if a else None, a.n_terms if a else 0, L.ptr(a.p0) if a else None,
                L.ptr(a.p1) if a else None, L.ptr(a.p2) if a else None, L.ptr(d.mapping) if d else None,
                d.n_terms if d else 0, L.ptr(d.p0) if d else None, L.ptr(d.p1) if d else None,

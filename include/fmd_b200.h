@@ -299,12 +299,14 @@ int fmd_prior_energy_forces(int kind, const float* pos, const int32_t* mapping, 
  * :265; simulation/specialize_prior.py:112-207).
  *   pair_ptr [n_nodes+1], pair_ent [n_pair_inc] of 16-byte records {other | kind<<28, p0, p1, p2}
  *     (kind FMD_PRIOR_BONDS: k, x0, V0; FMD_PRIOR_REPULSION: sigma, -, -), every pair listed under BOTH beads;
+ *     with pair_tab != NULL the records are 8 bytes {other | kind<<28, id} and (p0, p1, p2, -) = pair_tab[4 id ..]
+ *     (deduplicated parameter table, float4 per entry: halves the largest HBM stream outside the edge kernels);
  *   mb_ptr [n_nodes+1], mb_ent [n_mb_inc] = term | role<<28 | is_dihedral<<30, every term under each of its beads;
  *   ang_map [3,n_ang], dih_map [4,n_dih] int32 + flat parameter vectors (ang_v0 / dih_v0 nullable).
  * Outputs: e_atom [n_nodes] = the bead's share of its terms' energies (sum per molecule with
  * fmd_segment_sum), forces [n_nodes,3] written (accumulate_forces == 0) or added to. Any group may be NULL. */
-int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair_ptr, const void* pair_ent, const int32_t* mb_ptr,
-                   const int32_t* mb_ent, const int32_t* ang_map, int n_ang, const float* ang_k, const float* ang_x0,
+int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair_ptr, const void* pair_ent, const float* pair_tab,
+                   const int32_t* mb_ptr, const int32_t* mb_ent, const int32_t* ang_map, int n_ang, const float* ang_k, const float* ang_x0,
                    const float* ang_v0, const int32_t* dih_map, int n_dih, const float* dih_k1, const float* dih_k2,
                    const float* dih_v0, int n_degs, float* e_atom, float* forces, int accumulate_forces, void* stream);
 
