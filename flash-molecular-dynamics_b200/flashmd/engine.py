@@ -235,7 +235,7 @@ class ForceField:
         # W16A16 with the default widths runs the fused tcgen05 kernels (no [E,F] tensor in HBM);
         # other widths / the fp32 parity path use the materialised SIMT kernels.
         self.fused_tc = (precision == "w16a16" and F == 128 and H == 128 and R <= 64 and use_tensor_cores)
-        # fp32 parity path: dense layers as fp32-accurate 3xTF32 tensor-core GEMMs (fmd_linear_x3) instead of SIMT FMA
+        # fp32 parity path: dense layers as fp32-accurate BF16x3 (fp32-emulation) tensor-core GEMMs (fmd_linear_x3) instead of SIMT FMA
         self.x3 = precision == "fp32" and use_tensor_cores and os.environ.get("FMD_X3", "1") == "1"
         # node-level layers stay on the true-fp32 FMA kernel by default: they are 6 % of the step and the tensor-core
         # accumulation (round-toward-zero) leaves a coherent -1e-5 bias in the per-molecule energies (forces equal)
@@ -293,7 +293,7 @@ class ForceField:
                 args = args[:2] + (L.ptr(wt),) + args[3:]
             L.call("fmd_linear_tc", *args, int(wt is not None), self._st)
         elif x3:
-            # fp32 parity path: 3xTF32 split GEMM on the tensor cores (fp32-accurate), HBM-bound streaming kernel
+            # fp32 parity path: BF16x3 fp32-emulation GEMM on the tensor cores (fp32-accurate), HBM-bound streaming kernel
             L.call("fmd_linear_x3", L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(y), M, N, K, L.ptr(m_dev),
                    kw.get("epi_act", 0), L.ptr(kw.get("aux")), L.ptr(kw.get("res")), self._st)
         else:

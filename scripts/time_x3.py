@@ -1,4 +1,4 @@
-"""Per-shape timing of fmd_linear_x3 (3xTF32 GEMM) at the edge-level shapes of the fp32 path; prints achieved GB/s
+"""Per-shape timing of fmd_linear_x3 (BF16x3 fp32-emulation GEMM) at the edge-level shapes of the fp32 path; prints achieved GB/s
 of the algorithmic traffic (X read + Y written + aux/res read)."""
 import os, sys
 import torch

@@ -248,10 +248,10 @@ def test_dense_layers_tensor_core_tf32(M, K, N):
 
 @pytest.mark.parametrize("M,K,N", [(1000, 50, 128), (34432, 128, 128), (777, 128, 50), (300, 64, 64), (5, 2, 8),
                                    (70001, 128, 128), (513, 128, 1), (260, 100, 36)])
-def test_dense_layers_tensor_core_3xtf32(M, K, N):
-    """fmd_linear_x3 (tcgen05 kind::tf32, hi/lo split operands) is an fp32-ACCURATE GEMM: against torch fp64 it must
-    be as good as the true-fp32 FMA kernel (fmd_linear) up to a small factor, with every epilogue, ragged K / N,
-    a device-side row count, and rows beyond it left untouched."""
+def test_dense_layers_tensor_core_fp32_emulation(M, K, N):
+    """fmd_linear_x3 (tcgen05 kind::f16 on three exact bf16 slices per fp32 operand, six slice products) is an
+    fp32-ACCURATE GEMM: against torch fp64 it must be as good as the true-fp32 FMA kernel (fmd_linear) up to a small
+    factor, with every epilogue, ragged K / N, a device-side row count, and rows beyond it left untouched."""
     from flashmd import _lib as L
     g = torch.Generator().manual_seed(M + K + N)
     x = torch.randn((M, K), generator=g).to(DEV)
