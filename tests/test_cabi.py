@@ -60,3 +60,41 @@ def test_no_cpu_fallback():
         L.ptr(torch.zeros(3))
     with pytest.raises(RuntimeError):
         ForceField(None, [], torch.zeros(4, dtype=torch.long), torch.tensor([0, 4]))
+
+
+def test_prior_incidence_lists_packed_records_decode_to_the_inputs():
+    """Host logic of the owner-computes prior layout (engine.PriorCSR): every pair term is listed under both of its
+    beads, records are 8 bytes {other | kind << 28, id} and the deduplicated parameter table returns exactly the
+    parameters of the term (bonds k, x0, V0; repulsion sigma)."""
+    from flashmd import _lib as L
+    from flashmd.engine import PriorCSR, PriorTerm
+    g = torch.Generator().manual_seed(0)
+    n_nodes = 40
+    bi = torch.stack([torch.arange(0, n_nodes - 1), torch.arange(1, n_nodes)]).to(torch.int32)
+    kinds = torch.randint(0, 3, (bi.shape[1],), generator=g)
+    k = torch.tensor([10.0, 20.0, 30.0])[kinds]
+    x0 = torch.tensor([3.8, 4.0, 4.2])[kinds]
+    v0 = torch.zeros_like(k)
+    ri, rj = torch.triu_indices(n_nodes, n_nodes, offset=2)
+    rep = torch.stack([ri, rj]).to(torch.int32)
+    sigma = torch.tensor([3.0, 3.5])[torch.randint(0, 2, (rep.shape[1],), generator=g)]
+    priors = [PriorTerm(L.PRIOR_BONDS, bi, torch.zeros(bi.shape[1], dtype=torch.int32), k, x0, v0),
+              PriorTerm(L.PRIOR_REPULSION, rep, torch.zeros(rep.shape[1], dtype=torch.int32), sigma)]
+    csr = PriorCSR(priors, n_nodes, "cpu")
+    assert csr.pair_tab is not None and csr.pair_ent.shape[1] == 2 and csr.pair_tab.shape[0] <= 3 + 2
+    ptr, ent, tab = csr.pair_ptr.long(), csr.pair_ent, csr.pair_tab
+    assert int(ptr[-1]) == 2 * (bi.shape[1] + rep.shape[1])
+    want = {}
+    for (m, kind, ps) in ((bi, L.PRIOR_BONDS, (k, x0, v0)), (rep, L.PRIOR_REPULSION, (sigma, torch.zeros_like(sigma), torch.zeros_like(sigma)))):
+        for t in range(m.shape[1]):
+            a, b = int(m[0, t]), int(m[1, t])
+            want[(a, b)] = want[(b, a)] = (kind, tuple(float(p[t]) for p in ps))
+    seen = 0
+    for a in range(n_nodes):
+        for p in range(int(ptr[a]), int(ptr[a + 1])):
+            head, pid = int(ent[p, 0]), int(ent[p, 1])
+            other, kind = head & 0x0FFFFFFF, head >> 28
+            kw, pw = want[(a, other)]
+            assert kind == kw and tuple(float(v) for v in tab[pid, :3]) == pw
+            seen += 1
+    assert seen == len(want)
