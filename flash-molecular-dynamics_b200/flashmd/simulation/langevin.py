@@ -118,20 +118,33 @@ class LangevinSimulation(_Simulation):
 
 
 class OverdampedSimulation(_Simulation):
-    """Brownian dynamics x += dt D beta F + sqrt(2 D dt) xi (reference simulation/langevin.py:315-420), module path."""
+    """Overdamped Langevin (Brownian) dynamics with the reference's exact update (simulation/langevin.py:315-420):
+        D = 1 / (beta friction) per bead,  x += F D dt + sqrt(2 D dt) xi
+    (the drift carries no extra beta - the reference's own convention, reproduced for parity).  Masses and velocities
+    are not used.  Module path (CPU or CUDA operators); pinned by tests/golden/integrators_n54_b4.npz."""
 
-    def __init__(self, friction: float = 1.0, diffusion: float = 1.0, **kwargs: Any):
+    def __init__(self, friction: float = 1.0, **kwargs: Any):
         super().__init__(**kwargs)
-        self.diffusion = diffusion
-        self._dtau = diffusion * self.dt
+        assert friction > 0
+        self.friction = friction
+
+    def _attach_configurations(self, configurations: List, beta: Union[float, List[float]]):
+        super()._attach_configurations(configurations, beta)
+        if MASS_KEY in self.initial_data:
+            import warnings
+            warnings.warn("Masses were provided, but will not be used since an overdamped Langevin scheme is being "
+                          "used for integration.")
+        self.expanded_beta = self.beta.repeat_interleave(self.n_atoms)[:, None]
+        self.diffusion = 1 / self.expanded_beta / self.friction
+        self._dtau = self.diffusion * self.dt
 
     def _set_up_simulation(self, overwrite: bool = False):
         super()._set_up_simulation(overwrite)
         self._noise_buffer = torch.empty((self.n_sims * self.n_atoms, self.n_dims), dtype=self.dtype, device=self.device)
 
     def timestep(self, data, forces):
-        beta = self.beta.repeat_interleave(self.n_atoms)[:, None]
         noise = self._noise_buffer.normal_(generator=self.rng)
-        data[POSITIONS_KEY] = data[POSITIONS_KEY] + forces * self._dtau * beta + float(np.sqrt(2 * self._dtau)) * noise
+        dtau = self._dtau.to(device=forces.device, dtype=forces.dtype)
+        data[POSITIONS_KEY] = data[POSITIONS_KEY].detach() + forces * dtau + torch.sqrt(2 * dtau) * noise
         potential, forces = self.calculate_potential_and_forces(data)
         return data, potential, forces

@@ -47,6 +47,7 @@ from flashmd.models import (CosineCutoff, GaussianBasis, GradientsOut, StandardS
 from flashmd.neighbor_list.neighbor_list import make_neighbor_list  # noqa: E402
 from flashmd.prior import Dihedral, HarmonicAngles, HarmonicBonds, Repulsion  # noqa: E402
 from flashmd.simulation import LangevinSimulation, PTSimulation  # noqa: E402
+from flashmd.simulation import NVESimulation, OverdampedSimulation  # noqa: E402
 
 assert flashmd.__file__.startswith("/root/reference"), flashmd.__file__
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -211,6 +212,31 @@ def golden_langevin(system, model, schnet, configs, fname, n_steps=10):
     print(fname, arrs["coords"].shape, arrs["potential"].shape, list(arrs["files"]))
 
 
+def golden_integrators(system, model, configs, fname, n_steps=12):
+    """The other integrators of the reference, CPU module path, saved every step:
+    NVESimulation (simulation/velocity_verlet.py:12-95; deterministic given the Maxwell-Boltzmann velocities drawn from
+    the global RNG) and OverdampedSimulation (simulation/langevin.py:315-420; noise from torch.Generator(seed))."""
+    import tempfile
+    arrs = {}
+    for name, cls, kw in (("nve", NVESimulation, dict(dt=0.001)), ("overdamped", OverdampedSimulation, dict(dt=0.002, friction=2.0))):
+        tmp = tempfile.mkdtemp()
+        torch.manual_seed(4321)
+        sim = cls(n_timesteps=n_steps, save_interval=1, export_interval=n_steps, save_forces=True, save_energies=True,
+                  random_seed=777, device="cpu", dtype="single", filename="g", output_dir=tmp, specialize_priors=True,
+                  compile_model=False, gptq=None, **kw)
+        sim.attach_model_and_configurations(model, configs, beta=1.67)
+        if name == "nve":
+            arrs["nve.v0"] = sim.initial_data.velocities.numpy().copy()
+        sim.simulate()
+        arrs[f"{name}.coords"] = np.load(os.path.join(tmp, "g_coords_0000.npy"))
+        arrs[f"{name}.forces"] = np.load(os.path.join(tmp, "g_forces_0000.npy"))
+        arrs[f"{name}.potential"] = np.load(os.path.join(tmp, "g_potential_0000.npy"))
+        arrs[f"{name}.files"] = np.array(sorted(os.listdir(tmp)))
+    arrs["params"] = np.array([0.001, 0.002, 2.0, 1.67, 777, 4321], dtype=np.float64)   # dt_nve, dt_od, friction_od, beta, seed, global seed
+    np.savez_compressed(os.path.join(OUT, fname), **arrs)
+    print(fname, {k: v.shape for k, v in arrs.items() if k.endswith("coords")})
+
+
 def golden_pt(fname):
     """PTSimulation bookkeeping: pair sets, one Metropolis decision + swap with recorded uniforms
     (parallel_tempering.py:256-284, 368-481), and a short full run for the file set."""
@@ -279,10 +305,18 @@ def golden_known_answers(fname):
     print(fname, "ok")
 
 
+if __name__ == "__main__" and "--integrators" in sys.argv:
+    # only the integrator vectors (the static vectors are regenerated in memory, nothing else is rewritten)
+    _system = syn.synthetic_system(4, 54, seed=0, target_degree=30.0)
+    _model, _schnet, _configs = build_reference(_system, 128, 128, 50, 3, (128, 64), 0, 0.0)
+    golden_integrators(_system, _model, _configs, "integrators_n54_b4.npz", n_steps=12)
+    sys.exit(0)
+
 if __name__ == "__main__" and "--stats" not in sys.argv:
     golden_known_answers("known_answers.npz")
     system, model, schnet, configs = golden_static("schnet_n54_b4.npz", 4, 54, 0, 128, 128, 50, 3, (128, 64), 30.0)
     golden_langevin(system, model, schnet, configs, "langevin_n54_b4.npz", n_steps=10)
+    golden_integrators(system, model, configs, "integrators_n54_b4.npz", n_steps=12)
     golden_static("schnet_n24_b3_l2.npz", 3, 24, 3, 64, 64, 20, 2, (32,), 10.0, bias_scale=0.2)
     golden_pt("pt_n24.npz")
 

@@ -174,3 +174,33 @@ def test_nve_simulation_module_path_conserves_energy():
     sim.simulate()
     e_tot = sim.simulated_potential + sim.simulated_kinetic_energies
     assert np.abs(e_tot - e_tot[:, :1]).max() / sim.simulated_kinetic_energies.mean() < 2e-3
+
+
+def test_nve_and_overdamped_reproduce_reference_trajectories(tmp_path):
+    """The reference's other integrators step for step on the CPU module path:
+    NVESimulation (simulation/velocity_verlet.py:12-95) and OverdampedSimulation (simulation/langevin.py:315-420,
+    D = 1 / (beta friction), drift F D dt), against tests/golden/integrators_n54_b4.npz written by the UNMODIFIED
+    reference (oracle/make_golden.py --integrators)."""
+    from flashmd.simulation import NVESimulation, OverdampedSimulation
+    g = load_golden("schnet_n54_b4.npz")
+    t = load_golden("integrators_n54_b4.npz")
+    dt_nve, dt_od, fr_od, beta, seed, gseed = (float(v) for v in t["params"])
+    for name, cls, kw in (("nve", NVESimulation, dict(dt=dt_nve)), ("overdamped", OverdampedSimulation, dict(dt=dt_od, friction=fr_od))):
+        out = tmp_path / name
+        out.mkdir()
+        model, _, configs = dropin_model_from_golden(g)
+        torch.manual_seed(int(gseed))
+        sim = cls(n_timesteps=12, save_interval=1, export_interval=12, save_forces=True, save_energies=True,
+                  random_seed=int(seed), device="cpu", dtype="single", filename="g", output_dir=str(out),
+                  specialize_priors=True, compile_model=False, gptq=None, **kw)
+        sim.attach_model_and_configurations(model, configs, beta=beta)
+        if name == "nve":
+            assert np.array_equal(sim.initial_data.velocities.numpy(), t["nve.v0"])
+        sim.simulate()
+        coords = np.load(out / "g_coords_0000.npy")
+        assert coords.shape == t[f"{name}.coords"].shape == (4, 12, 54, 3)
+        assert rel_l2(coords, t[f"{name}.coords"]) < 1e-5, name
+        assert rel_l2(np.load(out / "g_potential_0000.npy"), t[f"{name}.potential"]) < 1e-4, name
+        assert rel_l2(np.load(out / "g_forces_0000.npy"), t[f"{name}.forces"]) < 2e-3, name     # chaotic growth over 12 steps
+        for f in t[f"{name}.files"]:
+            assert os.path.exists(out / str(f)), (name, f)
