@@ -1,6 +1,6 @@
 """Linear/activation stack with Xavier-uniform weights and zero biases (reference models/mlp.py:6-57,
 models/_module_init.py:4-28)."""
-from typing import List
+from typing import List, Optional
 
 import torch
 
@@ -36,3 +36,33 @@ class MLP(torch.nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.layers(x)
+
+
+class TypesMLP(torch.nn.Module):
+    """Per-atom energy MLP, optionally with a separate set of weights for every atom species (reference
+    models/mlp.py:60-121).  forward(features [N, in], data) -> [N, 1]."""
+    name = "TypesMLP"
+
+    def __init__(self, layer_widths: List[int], activation: torch.nn.Module = torch.nn.Tanh(),
+                 species: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.weights_per_species = species is not None
+        if self.weights_per_species:
+            self.register_buffer("species", torch.unique(species))
+            self.mlp = torch.nn.ModuleList([MLP(layer_widths, activation) for _ in self.species])
+        else:
+            self.species = None
+            self.mlp = MLP(layer_widths, activation)
+
+    def reset_parameters(self):
+        for mod in (self.mlp if self.weights_per_species else [self.mlp]):
+            mod.reset_parameters()
+
+    def forward(self, features, data):
+        if not self.weights_per_species:
+            return self.mlp(features)
+        yi = torch.zeros((features.shape[0], 1), dtype=features.dtype, device=features.device)
+        for sp, mlp in zip(self.species, self.mlp):
+            mask = data.atom_types == sp
+            yi[mask] = mlp(features[mask])
+        return yi

@@ -3,7 +3,7 @@ from typing import Dict
 
 import torch
 
-from ..geometry import compute_angles_cos, compute_distances, compute_torsions
+from ..geometry import compute_angles_cos, compute_angles_raw, compute_distances, compute_torsions
 from .base import _Prior, type_table
 
 
@@ -76,3 +76,50 @@ class HarmonicImpropers(Harmonic):
     @staticmethod
     def neighbor_list(topology) -> Dict:
         return _Prior._nl(HarmonicImpropers.name, 4, topology)
+
+
+class HarmonicAnglesRaw(Harmonic):
+    """Harmonic in theta itself (radians) (reference prior/harmonic.py:267-300; there the constructor forgets Harmonic's
+    `order` argument and raises - same signature here, working)."""
+    name = "angles"
+
+    def __init__(self, statistics, name="angles") -> None:
+        super().__init__(statistics, HarmonicAnglesRaw.name, order=3)
+        self.name = name
+
+    @staticmethod
+    def compute_features(pos, mapping):
+        return compute_angles_raw(pos, mapping)
+
+    @staticmethod
+    def neighbor_list(topology) -> Dict:
+        return _Prior._nl(HarmonicAnglesRaw.name, 3, topology)
+
+
+class GeneralBonds(Harmonic):
+    """Harmonic bonds registered under a caller-chosen name (several bond sets in one model; reference
+    prior/harmonic.py:407-428)."""
+    _order = 2
+    kernel_kind = None      # module path (not lowered to the fused step yet)
+
+    def __init__(self, statistics, name) -> None:
+        super().__init__(statistics, HarmonicBonds.name, order=GeneralBonds._order)
+        self.name = name
+
+    @staticmethod
+    def compute_features(pos, mapping):
+        return compute_distances(pos, mapping)
+
+
+class GeneralAngles(Harmonic):
+    """Harmonic cos(angle) terms registered under a caller-chosen name (reference prior/harmonic.py:430-450)."""
+    _order = 3
+    kernel_kind = None      # module path (not lowered to the fused step yet)
+
+    def __init__(self, statistics, name) -> None:
+        super().__init__(statistics, HarmonicAngles.name, order=GeneralAngles._order)
+        self.name = name
+
+    @staticmethod
+    def compute_features(pos, mapping):
+        return compute_angles_cos(pos, mapping)

@@ -46,6 +46,9 @@ from flashmd.data import AtomicData  # noqa: E402
 from flashmd.models import (CosineCutoff, GaussianBasis, GradientsOut, StandardSchNet, SumOut)  # noqa: E402
 from flashmd.neighbor_list.neighbor_list import make_neighbor_list  # noqa: E402
 from flashmd.prior import Dihedral, HarmonicAngles, HarmonicBonds, Repulsion  # noqa: E402
+from flashmd.prior import (GeneralAngles, GeneralBonds, HarmonicImpropers, Polynomial, QuarticAngles,  # noqa: E402
+                           RestrictedQuartic)
+from flashmd.prior.harmonic import HarmonicAnglesRaw  # noqa: E402
 from flashmd.simulation import LangevinSimulation, PTSimulation  # noqa: E402
 from flashmd.simulation import NVESimulation, OverdampedSimulation  # noqa: E402
 
@@ -237,6 +240,43 @@ def golden_integrators(system, model, configs, fname, n_steps=12):
     print(fname, {k: v.shape for k, v in arrs.items() if k.endswith("coords")})
 
 
+def golden_extra_priors(system, fname):
+    """Energies (per molecule) and forces of the prior classes the benchmark system does not use, evaluated by the
+    UNMODIFIED reference (GradientsOut autograd, fp32 and fp64) on the golden 4 x 54-bead system; statistics from
+    oracle/extra_prior_stats.py so that the drop-in test can rebuild the same objects."""
+    import extra_prior_stats as X
+    ty = system["atom_types"]
+    kb, ka, kd = X.type_keys(ty, system["bonds"]), X.type_keys(ty, system["angles"]), X.type_keys(ty, system["dihedrals"])
+    priors = {
+        "gbonds": (GeneralBonds(X.harmonic_stats(kb, 3.6, 4.0), "gbonds"), system["bonds"], 2),
+        "gangles": (GeneralAngles(X.harmonic_stats(ka, -0.6, 0.2), "gangles"), system["angles"], 3),
+        # HarmonicAnglesRaw cannot be constructed in the reference (its __init__ omits Harmonic's `order`, harmonic.py:287)
+        # HarmonicImpropers.forward raises in the reference (data2features is a @staticmethod taking self, harmonic.py:313)
+        "poly_bonds": (Polynomial(X.polynomial_stats(kb), "poly_bonds", order=2, n_degs=4), system["bonds"], 2),
+        "quartic_angles": (QuarticAngles(X.polynomial_stats(ka), name="quartic_angles"), system["angles"], 3),
+        "restricted": (RestrictedQuartic(X.restricted_quartic_stats(ka), name="restricted"), system["angles"], 3),
+    }
+    # Polynomial itself has no feature function (the reference's users subclass it): distances for the bond set
+    from flashmd.geometry import compute_distances
+    priors["poly_bonds"][0].data2features = lambda data, p=priors["poly_bonds"][0]: compute_distances(
+        data.pos, data.neighbor_list[p.name]["index_mapping"])
+    arrs = {}
+    for name, (prior, mapping, order) in priors.items():
+        nl_name = prior.name
+        configs = [AtomicData.from_points(pos=torch.from_numpy(system["pos"][b].copy()), atom_types=torch.from_numpy(ty),
+                                          masses=torch.from_numpy(system["masses"]),
+                                          neighborlist={nl_name: make_neighbor_list(nl_name, order, torch.from_numpy(mapping))})
+                   for b in range(system["pos"].shape[0])]
+        model = SumOut(torch.nn.ModuleDict({nl_name: GradientsOut(prior)}))
+        for dt, tag in ((torch.float32, "ref32"), (torch.float64, "ref64")):
+            out, _ = eval_reference(model, configs, dt)
+            arrs[f"{tag}.{name}.energy"] = out["energy.total"]
+            arrs[f"{tag}.{name}.forces"] = out["forces.total"]
+        model.to(torch.float32)
+    np.savez_compressed(os.path.join(OUT, fname), **arrs)
+    print(fname, sorted(k for k in arrs if k.startswith("ref64") and k.endswith("energy")))
+
+
 def golden_pt(fname):
     """PTSimulation bookkeeping: pair sets, one Metropolis decision + swap with recorded uniforms
     (parallel_tempering.py:256-284, 368-481), and a short full run for the file set."""
@@ -310,6 +350,10 @@ if __name__ == "__main__" and "--integrators" in sys.argv:
     _system = syn.synthetic_system(4, 54, seed=0, target_degree=30.0)
     _model, _schnet, _configs = build_reference(_system, 128, 128, 50, 3, (128, 64), 0, 0.0)
     golden_integrators(_system, _model, _configs, "integrators_n54_b4.npz", n_steps=12)
+    sys.exit(0)
+
+if __name__ == "__main__" and "--extra-priors" in sys.argv:
+    golden_extra_priors(syn.synthetic_system(4, 54, seed=0, target_degree=30.0), "extra_priors_n54_b4.npz")
     sys.exit(0)
 
 if __name__ == "__main__" and "--stats" not in sys.argv:

@@ -204,3 +204,47 @@ def test_nve_and_overdamped_reproduce_reference_trajectories(tmp_path):
         assert rel_l2(np.load(out / "g_forces_0000.npy"), t[f"{name}.forces"]) < 2e-3, name     # chaotic growth over 12 steps
         for f in t[f"{name}.files"]:
             assert os.path.exists(out / str(f)), (name, f)
+
+
+def test_extra_prior_classes_match_reference():
+    """Prior classes beyond the benchmark's four: GeneralBonds, GeneralAngles,
+    Polynomial, QuarticAngles, RestrictedQuartic - per-molecule energies and autograd forces against the UNMODIFIED
+    reference (tests/golden/extra_priors_n54_b4.npz, oracle/make_golden.py --extra-priors); statistics tables shared
+    through oracle/extra_prior_stats.py.  (HarmonicAnglesRaw and HarmonicImpropers cannot run in the reference itself:
+    harmonic.py:287 / :313.)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import extra_prior_stats as X
+    from flashmd import synthetic
+    from flashmd.data import AtomicData
+    from flashmd.geometry import compute_distances
+    from flashmd.models import GradientsOut, SumOut
+    from flashmd.neighbor_list import make_neighbor_list
+    from flashmd.prior import GeneralAngles, GeneralBonds, Polynomial, QuarticAngles, RestrictedQuartic
+    from flashmd.simulation import LangevinSimulation
+    t = load_golden("extra_priors_n54_b4.npz")
+    system = synthetic.synthetic_system(4, 54, seed=0, target_degree=30.0)
+    ty = system["atom_types"]
+    kb, ka = X.type_keys(ty, system["bonds"]), X.type_keys(ty, system["angles"])
+    poly = Polynomial(X.polynomial_stats(kb), "poly_bonds", order=2, n_degs=4)
+    poly.compute_features = staticmethod(compute_distances)
+    priors = {
+        "gbonds": (GeneralBonds(X.harmonic_stats(kb, 3.6, 4.0), "gbonds"), system["bonds"], 2),
+        "gangles": (GeneralAngles(X.harmonic_stats(ka, -0.6, 0.2), "gangles"), system["angles"], 3),
+        "poly_bonds": (poly, system["bonds"], 2),
+        "quartic_angles": (QuarticAngles(X.polynomial_stats(ka), name="quartic_angles"), system["angles"], 3),
+        "restricted": (RestrictedQuartic(X.restricted_quartic_stats(ka), name="restricted"), system["angles"], 3),
+    }
+    for name, (prior, mapping, order) in priors.items():
+        configs = [AtomicData.from_points(pos=torch.from_numpy(system["pos"][b].copy()), atom_types=torch.from_numpy(ty),
+                                          masses=torch.from_numpy(system["masses"]),
+                                          neighborlist={prior.name: make_neighbor_list(prior.name, order, torch.from_numpy(mapping))})
+                   for b in range(4)]
+        model = SumOut(torch.nn.ModuleDict({prior.name: GradientsOut(prior)}))
+        for dt, tag, tol in ((torch.float64, "ref64", 1e-12), (torch.float32, "ref32", 2e-5)):
+            data = LangevinSimulation.collate(configs)
+            data.pos = data.pos.to(dt)
+            data.out = {}
+            data = model.to(dt)(data)
+            assert rel_l2(data.out["energy"].detach().numpy(), t[f"{tag}.{name}.energy"]) < tol, (name, tag)
+            assert rel_l2(data.out["forces"].detach().numpy(), t[f"{tag}.{name}.forces"]) < tol * 10, (name, tag)
