@@ -41,8 +41,10 @@ class Dihedral(FourierSeries):
     name = "dihedrals"
     kernel_kind = 2
 
-    def __init__(self, statistics, n_degs: int = 6) -> None:
-        super().__init__(statistics, Dihedral.name, n_degs=n_degs, order=4)
+    _order = 4
+
+    def __init__(self, statistics, n_degs: int = 3, name: str = "dihedrals") -> None:    # reference defaults (:448-456)
+        super().__init__(statistics, name=name, n_degs=n_degs, order=self._order)
 
     @staticmethod
     def compute_features(pos, mapping):

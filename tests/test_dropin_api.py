@@ -248,3 +248,27 @@ def test_extra_prior_classes_match_reference():
             data = model.to(dt)(data)
             assert rel_l2(data.out["energy"].detach().numpy(), t[f"{tag}.{name}.energy"]) < tol, (name, tag)
             assert rel_l2(data.out["forces"].detach().numpy(), t[f"{tag}.{name}.forces"]) < tol * 10, (name, tag)
+
+
+def test_constructor_signatures_follow_the_reference():
+    """Objects a user (or a pickled model) constructs directly keep the reference's signatures: Dihedral(statistics,
+    n_degs=3, name=...), GPTQW16A16FilterNetwork(in, hidden, out) / .from_mlp, GPTQW16A16OutputNetwork(in, h1, h2, out) /
+    .from_mlp with weight<i> / bias<i> attributes stored [in, out] in fp16 (reference models/gptq.py:51-76, 215-256)."""
+    from flashmd.models import MLP
+    from flashmd.models.gptq import GPTQW16A16FilterNetwork, GPTQW16A16OutputNetwork
+    from flashmd.prior import Dihedral
+    st = {(1, 2, 3, 4): {"k1s": {f"k1_{i}": 0.1 * i for i in (1, 2, 3)}, "k2s": {f"k2_{i}": 0.2 * i for i in (1, 2, 3)}, "v_0": 0.5}}
+    d = Dihedral(st, name="phi")
+    assert d.name == "phi" and d.n_degs == 3 and d.order == 4
+    f = GPTQW16A16FilterNetwork(50, 128, 128)
+    assert f.weight0.shape == (50, 128) and f.weight0.dtype == torch.float16 and f.bias0.shape == (128,)
+    assert f.weight1.shape == (128, 128) and (f.in_features, f.hidden_features, f.out_features) == (50, 128, 128)
+    mlp = MLP([50, 128, 128], torch.nn.Tanh(), last_bias=False)
+    g = GPTQW16A16FilterNetwork.from_mlp(mlp)
+    lin = [m for m in mlp.layers if isinstance(m, torch.nn.Linear)]
+    assert torch.equal(g.weight0, lin[0].weight.detach().t().half()) and torch.equal(g.weight1, lin[1].weight.detach().t().half())
+    o = GPTQW16A16OutputNetwork(128, 128, 64, 1)
+    assert o.weight0.shape == (128, 128) and o.weight1.shape == (128, 64) and o.weight2.shape == (64, 1)
+    assert o.bias0.shape == (128,) and o.bias1.shape == (64,)
+    o2 = GPTQW16A16OutputNetwork.from_mlp(MLP([128, 128, 64, 1], torch.nn.Tanh(), last_bias=False))
+    assert o2.n_layers == 3 and o2.weight2.dtype == torch.float16
