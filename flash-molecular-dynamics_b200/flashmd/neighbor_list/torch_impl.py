@@ -82,8 +82,10 @@ def _radius_graph_torch(pos: torch.Tensor, ptr: torch.Tensor, rcut: float, max_n
     return torch.cat(out, dim=1) if out else torch.zeros((2, 0), dtype=torch.long)
 
 
-def torch_neighbor_list(data, rcut: float, self_interaction: bool = False, max_num_neighbors: int = 1000) -> torch.Tensor:
-    """edge_index [2,E] of a collated batch (reference torch_impl.py:175-226, no-PBC branch)."""
+def torch_neighbor_list(data, rcut: float, self_interaction: bool = False, num_workers: int = 1,
+                        max_num_neighbors: int = 1000) -> torch.Tensor:
+    """edge_index [2,E] of a collated batch (reference torch_impl.py:175-226, no-PBC branch; `num_workers` is accepted
+    for signature compatibility and ignored)."""
     if self_interaction:
         raise NotImplementedError("self_interaction=True is not supported (the reference never passes it)")
     pos = data.pos
@@ -91,3 +93,15 @@ def torch_neighbor_list(data, rcut: float, self_interaction: bool = False, max_n
     if pos.is_cuda:
         return radius_graph_csr(pos, ptr, rcut, max_num_neighbors)["edge_index"]
     return _radius_graph_torch(pos, ptr, rcut, max_num_neighbors)
+
+
+def torch_neighbor_list_no_pbc(data, rcut: float, self_interaction: bool = False, num_workers: int = 1,
+                               max_num_neighbors: int = 1000) -> torch.Tensor:
+    """Reference torch_impl.py:175-226 by its own name."""
+    return torch_neighbor_list(data, rcut, self_interaction, num_workers, max_num_neighbors)
+
+
+def torch_neighbor_list_pbc(data, rcut: float, self_interaction: bool = False, num_workers: int = 1,
+                            max_num_neighbors: int = 1000):
+    raise NotImplementedError("periodic neighbour lists are out of scope (coarse-grained proteins are simulated without a "
+                              "cell; reference torch_impl.py:252-329)")

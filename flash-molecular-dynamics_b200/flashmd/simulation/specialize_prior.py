@@ -6,10 +6,11 @@ because user scripts and saved configs call it."""
 from typing import List
 
 
-def condense_all_priors_for_simulation(model, configurations: List):
-    """Returns (model, configurations) like the reference (specialize_prior.py:76-109)."""
-    return model, configurations
+def condense_all_priors_for_simulation(priors, data_list: List):
+    """Returns (priors, data_list) like the reference (specialize_prior.py:76-109)."""
+    return priors, data_list
 
 
-def condense_prior_for_simulation(prior, configurations: List):
-    return prior
+def condense_prior_for_simulation(TargetPrior, priors, data_list: List):
+    """Reference specialize_prior.py:112-207 merges all priors of class `TargetPrior` into one static module."""
+    return priors, data_list

@@ -3,6 +3,17 @@ import yaml
 KB_KCAL = 0.0019872041   # kcal/mol/K
 
 
+KBOLTZMANN = 1.38064852e-23   # J/K          (reference simulation/base.py:36-38)
+AVOGADRO = 6.022140857e23
+JPERKCAL = 4184
+
+
+def calc_beta_from_temperature(temp):
+    """Temperature(s) in Kelvin -> inverse temperature(s) in mol/kcal (reference simulation/utils.py)."""
+    import numpy as np
+    return JPERKCAL / KBOLTZMANN / AVOGADRO / np.array(temp)
+
+
 def beta_from_temperature(temperature_K: float) -> float:
     return 1.0 / (KB_KCAL * temperature_K)
 
