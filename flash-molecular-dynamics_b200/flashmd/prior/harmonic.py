@@ -1,4 +1,5 @@
 """k (x - x0)^2 priors on distances and cos(angle) (reference prior/harmonic.py:23-330)."""
+import math
 from typing import Dict
 
 import torch
@@ -123,3 +124,24 @@ class GeneralAngles(Harmonic):
     @staticmethod
     def compute_features(pos, mapping):
         return compute_angles_cos(pos, mapping)
+
+
+class ShiftedPeriodicHarmonicImpropers(Harmonic):
+    """Harmonic improper torsions for distributions centred on +-pi (e.g. omega): torsions below zero are shifted by 2 pi
+    and pi is subtracted, so the harmonic well sits at the discontinuity (reference prior/harmonic.py:327-405)."""
+    name = "impropers"
+    _order = 4
+
+    def __init__(self, statistics) -> None:
+        super().__init__(statistics, ShiftedPeriodicHarmonicImpropers.name, order=4)
+
+    @staticmethod
+    def compute_features(pos, mapping):
+        phi = compute_torsions(pos, mapping)
+        # the reference's pi is torch.tensor(pi), i.e. the FLOAT32 value 3.14159274..., also on its fp64 path (harmonic.py:20)
+        pi32 = float(torch.tensor(math.pi, dtype=torch.float32))
+        return torch.where(phi < 0, phi + 2 * pi32, phi) - pi32
+
+    @staticmethod
+    def neighbor_list(topology) -> Dict:
+        return _Prior._nl(HarmonicImpropers.name, 4, topology)

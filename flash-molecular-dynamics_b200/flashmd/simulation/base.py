@@ -151,6 +151,15 @@ class _Simulation:
         self._attach_model(model)
         self._attach_configurations(configurations, beta)
 
+    def attach_model(self, model: torch.nn.Module):
+        warnings.warn("using 'attach_model' is deprecated, use 'attach_model_and_configurations' instead.", DeprecationWarning)
+        self._attach_model(model)
+
+    def attach_configurations(self, configurations: List[AtomicData], beta: Union[float, List[float]]):
+        warnings.warn("using 'attach_configurations' is deprecated, use 'attach_model_and_configurations' instead.",
+                      DeprecationWarning)
+        self._attach_configurations(configurations, beta)
+
     def _attach_model(self, model: torch.nn.Module):
         self.model = deepcopy(model).eval().to(device=self.device, dtype=self.dtype)
         for p in self.model.parameters():

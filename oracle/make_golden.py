@@ -48,7 +48,7 @@ from flashmd.neighbor_list.neighbor_list import make_neighbor_list  # noqa: E402
 from flashmd.prior import Dihedral, HarmonicAngles, HarmonicBonds, Repulsion  # noqa: E402
 from flashmd.prior import (GeneralAngles, GeneralBonds, HarmonicImpropers, Polynomial, QuarticAngles,  # noqa: E402
                            RestrictedQuartic)
-from flashmd.prior.harmonic import HarmonicAnglesRaw  # noqa: E402
+from flashmd.prior.harmonic import HarmonicAnglesRaw, ShiftedPeriodicHarmonicImpropers  # noqa: E402
 from flashmd.simulation import LangevinSimulation, PTSimulation  # noqa: E402
 from flashmd.simulation import NVESimulation, OverdampedSimulation  # noqa: E402
 
@@ -255,6 +255,7 @@ def golden_extra_priors(system, fname):
         "poly_bonds": (Polynomial(X.polynomial_stats(kb), "poly_bonds", order=2, n_degs=4), system["bonds"], 2),
         "quartic_angles": (QuarticAngles(X.polynomial_stats(ka), name="quartic_angles"), system["angles"], 3),
         "restricted": (RestrictedQuartic(X.restricted_quartic_stats(ka), name="restricted"), system["angles"], 3),
+        "shifted_impropers": (ShiftedPeriodicHarmonicImpropers(X.harmonic_stats(kd, -0.5, 0.5)), system["dihedrals"], 4),
     }
     # Polynomial itself has no feature function (the reference's users subclass it): distances for the bond set
     from flashmd.geometry import compute_distances

@@ -220,12 +220,13 @@ def test_extra_prior_classes_match_reference():
     from flashmd.geometry import compute_distances
     from flashmd.models import GradientsOut, SumOut
     from flashmd.neighbor_list import make_neighbor_list
-    from flashmd.prior import GeneralAngles, GeneralBonds, Polynomial, QuarticAngles, RestrictedQuartic
+    from flashmd.prior import (GeneralAngles, GeneralBonds, Polynomial, QuarticAngles, RestrictedQuartic,
+                               ShiftedPeriodicHarmonicImpropers)
     from flashmd.simulation import LangevinSimulation
     t = load_golden("extra_priors_n54_b4.npz")
     system = synthetic.synthetic_system(4, 54, seed=0, target_degree=30.0)
     ty = system["atom_types"]
-    kb, ka = X.type_keys(ty, system["bonds"]), X.type_keys(ty, system["angles"])
+    kb, ka, kd = X.type_keys(ty, system["bonds"]), X.type_keys(ty, system["angles"]), X.type_keys(ty, system["dihedrals"])
     poly = Polynomial(X.polynomial_stats(kb), "poly_bonds", order=2, n_degs=4)
     poly.compute_features = staticmethod(compute_distances)
     priors = {
@@ -234,6 +235,7 @@ def test_extra_prior_classes_match_reference():
         "poly_bonds": (poly, system["bonds"], 2),
         "quartic_angles": (QuarticAngles(X.polynomial_stats(ka), name="quartic_angles"), system["angles"], 3),
         "restricted": (RestrictedQuartic(X.restricted_quartic_stats(ka), name="restricted"), system["angles"], 3),
+        "shifted_impropers": (ShiftedPeriodicHarmonicImpropers(X.harmonic_stats(kd, -0.5, 0.5)), system["dihedrals"], 4),
     }
     for name, (prior, mapping, order) in priors.items():
         configs = [AtomicData.from_points(pos=torch.from_numpy(system["pos"][b].copy()), atom_types=torch.from_numpy(ty),
