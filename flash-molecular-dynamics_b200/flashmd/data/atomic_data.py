@@ -83,6 +83,17 @@ class AtomicData:
 
     # ---- constructors
     @staticmethod
+    def from_ase(frame, energy_tag: str = ENERGY_KEY, force_tag: str = FORCE_KEY) -> "AtomicData":
+        """From an ase.Atoms-like object (duck-typed: get_atomic_numbers / get_positions / get_masses / get_pbc /
+        get_cell, .info, .arrays), as reference data/atomic_data.py:106-152: types = atomic numbers, tag / energy from
+        `frame.info`, forces from `frame.arrays`."""
+        pos = torch.from_numpy(frame.get_positions())
+        return AtomicData.from_points(
+            pos=pos, atom_types=torch.from_numpy(frame.get_atomic_numbers()), masses=torch.from_numpy(frame.get_masses()),
+            pbc=torch.from_numpy(frame.get_pbc()), cell=torch.tensor(frame.get_cell().tolist(), dtype=pos.dtype),
+            tag=frame.info.get("tag"), energy=frame.info.get(energy_tag), forces=frame.arrays.get(force_tag))
+
+    @staticmethod
     def from_points(pos: torch.Tensor, atom_types: torch.Tensor, masses: Optional[torch.Tensor] = None,
                     pbc=None, cell=None, tag: Optional[str] = None, energy=None, forces=None,
                     velocities: Optional[torch.Tensor] = None,
@@ -107,8 +118,9 @@ class AtomicData:
             d[FORCE_KEY] = torch.as_tensor(forces)
         if tag is not None:
             d[TAG_KEY] = tag
-        if pbc is not None or cell is not None:
+        if pbc is not None and bool(torch.as_tensor(pbc).any()):
             raise NotImplementedError("periodic systems are out of scope of the B200 hot path (DESIGN.md section 7)")
+        # a non-periodic frame may still carry (ignored) cell vectors, e.g. from ASE
         d[NEIGHBOR_LIST_KEY] = neighborlist if neighborlist is not None else {}
         d.update(kwargs)
         return AtomicData(**d)
