@@ -221,11 +221,13 @@ def golden_integrators(system, model, configs, fname, n_steps=12):
     the global RNG) and OverdampedSimulation (simulation/langevin.py:315-420; noise from torch.Generator(seed))."""
     import tempfile
     arrs = {}
-    for name, cls, kw in (("nve", NVESimulation, dict(dt=0.001)), ("overdamped", OverdampedSimulation, dict(dt=0.002, friction=2.0))):
+    for name, cls, kw in (("nve", NVESimulation, dict(dt=0.001)), ("overdamped", OverdampedSimulation, dict(dt=0.002, friction=2.0)),
+                          ("langevin_double", LangevinSimulation, dict(dt=0.004, friction=1.0, dtype="double"))):
         tmp = tempfile.mkdtemp()
         torch.manual_seed(4321)
+        kw = dict(dtype="single") | kw
         sim = cls(n_timesteps=n_steps, save_interval=1, export_interval=n_steps, save_forces=True, save_energies=True,
-                  random_seed=777, device="cpu", dtype="single", filename="g", output_dir=tmp, specialize_priors=True,
+                  random_seed=777, device="cpu", filename="g", output_dir=tmp, specialize_priors=True,
                   compile_model=False, gptq=None, **kw)
         sim.attach_model_and_configurations(model, configs, beta=1.67)
         if name == "nve":
