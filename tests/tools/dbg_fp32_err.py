@@ -1,7 +1,7 @@
 """fp32 parity path at cfg2 shape: energy / force error of the first molecules against the fp64 oracle."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "flash-molecular-dynamics_b200"), os.path.join(ROOT, "tests")]
 from oracle import fmd_oracle as O
 from helpers import rel_l2

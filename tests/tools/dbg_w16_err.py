@@ -1,7 +1,7 @@
 """W16A16 fused path against the oracle's W16A16 rounding model and against fp32, golden system + cfg2-shaped system."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "flash-molecular-dynamics_b200"), os.path.join(ROOT, "tests")]
 from oracle import fmd_oracle as O
 from helpers import golden_params, golden_system, load_golden, rel_l2
