@@ -169,7 +169,7 @@ def test_trajectory_statistics_vs_reference_10k_steps(gptq):
     # frame ACROSS the 64 independent molecules (insensitive to the drift) and averaged over frames.
     # This synthetic model at dt = 0.004 has rare heating events (a repulsive contact integrated with a large step): the
     # UNMODIFIED reference's own sample holds KE spikes up to 139 (mean 48.8, 34 of 8000 samples above 75) and ours, with
-    # 8x the molecules, up to ~10^3 for some velocity seeds (scripts/dbg_stats.py).  Means and ROBUST widths are compared:
+    # 8x the molecules, up to ~10^3 for some velocity seeds (tests/tools/dbg_stats.py).  Means and ROBUST widths are compared:
     # the median over frames of the cross-molecule std, and the MAD-based width of the whole sample.
     canon = ke_ref.mean() * np.sqrt(2.0 / (3 * 54))
     per_frame = np.median(ke_our.std(axis=0, ddof=1))
@@ -199,7 +199,7 @@ def test_nve_energy_conservation_fused_engine(gptq, drift_bar, slope_bar):
     Initial velocities are pinned (seeded CPU generator): attach draws them from the global RNG like the reference,
     and the size of the integration error depends strongly on the initial condition (close repulsive contacts): with
     the TRUE-fp32 FMA GEMMs the drift at dt = 0.001 is 1e-4 ... 2e-2 of the mean kinetic energy over five seeds, and it
-    vanishes with the time step (seed 100: 1.8e-2, 7.7e-3, 8e-4 at dt, dt/2, dt/4; scripts/dbg_nve.py, dbg_nve2.py),
+    vanishes with the time step (seed 100: 1.8e-2, 7.7e-3, 8e-4 at dt, dt/2, dt/4; tests/tools/dbg_nve.py, dbg_nve2.py),
     which is the signature of integrator error, not of inconsistent forces.  The test therefore runs at dt/4."""
     from flashmd.simulation import NVESimulation
     g = load_golden("schnet_n54_b4.npz")

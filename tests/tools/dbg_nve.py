@@ -2,7 +2,7 @@
 for the GEMM variants: prints drift / slope in units of the mean kinetic energy."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "flash-molecular-dynamics_b200"), os.path.join(ROOT, "tests")]
 from helpers import dropin_model_from_golden, load_golden
 from flashmd.simulation import NVESimulation

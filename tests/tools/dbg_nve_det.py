@@ -1,7 +1,7 @@
 """Is an NVE run through the fused engine bitwise reproducible (same process, same inputs)?"""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "flash-molecular-dynamics_b200"), os.path.join(ROOT, "tests")]
 from helpers import dropin_model_from_golden, load_golden
 from flashmd.simulation import NVESimulation
