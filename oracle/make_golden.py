@@ -17,6 +17,7 @@ Files written:
   langevin_n54_b4.npz  10 BAOAB steps of LangevinSimulation with the noise that was drawn
   pt_n24.npz           PTSimulation exchange bookkeeping (pairs, swaps) for 3 betas x 2 configs
   known_answers.npz    cutoff / basis known-answer values from the reference's own unit tests
+  schnet_n40_b2_l5.npz (--l5) cfg5's depth: 5 interaction blocks, default widths, 2 x 40 beads
 """
 import importlib.util
 import os
@@ -353,6 +354,11 @@ if __name__ == "__main__" and "--integrators" in sys.argv:
     _system = syn.synthetic_system(4, 54, seed=0, target_degree=30.0)
     _model, _schnet, _configs = build_reference(_system, 128, 128, 50, 3, (128, 64), 0, 0.0)
     golden_integrators(_system, _model, _configs, "integrators_n54_b4.npz", n_steps=12)
+    sys.exit(0)
+
+if __name__ == "__main__" and "--l5" in sys.argv:
+    # cfg5's depth (5 interaction blocks, default widths) on a small system: 2 x 40 beads
+    golden_static("schnet_n40_b2_l5.npz", 2, 40, 7, 128, 128, 50, 5, (128, 64), 20.0)
     sys.exit(0)
 
 if __name__ == "__main__" and "--extra-priors" in sys.argv:
