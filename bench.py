@@ -420,7 +420,7 @@ def kernel_roofline(ff, eng, args, E):
         except Exception:
             traffic = {}
     how = "CUDA events around each launch of an eager (non-graph) step, same stream, averaged over 3 steps"
-    if "fmd_filter_cfconv_fwd2" in timings:
+    if "fmd_filter_cfconv_fwd" in timings:
         def tensor_roof(cname, kname, flops):
             ms = avg_ms(cname)
             ach = flops / (ms * 1e-3) / 1e12
@@ -431,15 +431,16 @@ def kernel_roofline(ff, eng, args, E):
                                    f"{tf_burst:.0f}",
                     "how": how}
         flops = 2.0 * E * F * (R + F)
-        roof = tensor_roof("fmd_filter_cfconv_fwd2", "filter_cfconv_fwd2_kernel", flops)
-        roof["also"] = [tensor_roof("fmd_filter_cfconv_bwd2", "filter_cfconv_bwd2_kernel", flops)]
+        roof = tensor_roof("fmd_filter_cfconv_fwd", "filter_cfconv_fwd_kernel", flops)
+        roof["also"] = [tensor_roof("fmd_filter_cfconv_bwd", "filter_cfconv_bwd_kernel", flops)]
         # by time per step the backward kernel is the dominant one: report it first
         if roof["also"][0]["avg_launch_ms"] * roof["also"][0]["launches_per_step"] > roof["avg_launch_ms"] * roof["launches_per_step"]:
             first = roof.pop("also")[0]
             first["also"] = [roof]
             roof = first
-        roof["note"] = ("fp16 tcgen05 GEMMs fused with the tanh / gather / segment-reduce epilogues; the kernel is "
-                        "bound by the SIMT epilogue (MUFU + issue slots), not by the tensor pipe: see DESIGN.md")
+        roof["note"] = ("fp16 tcgen05 GEMMs fused with the tanh / gather / segment-reduce epilogues; the kernels are bound by "
+                        "their SIMT roles (E x F tanh on the MUFU pipe, E x F multiply-accumulate, role-to-role hand-off "
+                        "latency), not by the tensor pipe: see DESIGN.md; avg_launch_ms of the forward includes its fix-up launch")
     else:
         cf_ms = avg_ms("fmd_cfconv_csr")
         alg = E * F * b + 4 * N * F + 4 * N * F + 4 * E + 4 * E + 4 * (N + 1)

@@ -82,6 +82,7 @@ struct RbfRecurrence {
   float a;      // -2 delta g2
   float b;      // g2 delta^2
   float cstep;  // ex2(2 g2 delta^2)
+  float delta;  // centre spacing
   int uniform;  // centres equally spaced (else the direct evaluation is used)
 };
 __device__ __forceinline__ RbfRecurrence make_rbf_recurrence(const float* sCen, int R, float g2) {
@@ -92,6 +93,7 @@ __device__ __forceinline__ RbfRecurrence make_rbf_recurrence(const float* sCen, 
   rr.a = -2.0f * delta * g2;
   rr.b = g2 * delta * delta;
   rr.cstep = ex2_approx(2.0f * g2 * delta * delta);
+  rr.delta = delta;
   rr.uniform = ok;
   return rr;
 }

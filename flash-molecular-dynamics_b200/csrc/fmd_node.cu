@@ -345,21 +345,6 @@ extern "C" int fmd_out_head(const void* y, const void* w, int dt, int n_nodes, i
   return FMD_OK;
 }
 
-// L2 warm-up of a buffer that a later gather kernel will read in a latency-bound pattern
-__global__ void __launch_bounds__(256) l2_prefetch_kernel(const char* __restrict__ p, size_t bytes) {
-  const size_t line = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128;
-  if (line < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + line));
-}
-
-extern "C" int fmd_l2_prefetch(const void* ptr, uint64_t bytes, void* stream) {
-  FMD_REQUIRE(ptr || bytes == 0, "fmd_l2_prefetch: bad arguments");
-  if (bytes == 0) return FMD_OK;
-  const size_t lines = (bytes + 127) / 128;
-  l2_prefetch_kernel<<<fmd_div_up((long long)lines, 256), 256, 0, (cudaStream_t)stream>>>((const char*)ptr, bytes);
-  FMD_CHECK_LAUNCH();
-  return FMD_OK;
-}
-
 __global__ void increment_u64_kernel(uint64_t* p) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *p += 1;
 }

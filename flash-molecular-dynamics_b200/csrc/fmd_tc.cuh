@@ -44,7 +44,12 @@ __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
-    if (!done && ++spins > (1u << 20)) asm volatile("trap;");
+    if (!done) {
+      if (++spins > (1u << 20)) asm volatile("trap;");
+#ifdef FMD_WAIT_BACKOFF_NS
+      __nanosleep(FMD_WAIT_BACKOFF_NS);
+#endif
+    }
   } while (!done);
 }
 

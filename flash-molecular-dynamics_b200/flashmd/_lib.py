@@ -54,17 +54,12 @@ _SIGS = {
                                 c_float, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
     "fmd_filter_cfconv_fwd": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p,
-                               c_void_p, c_void_p, c_void_p], c_int),
-    "fmd_filter_cfconv_fwd2": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p,
-                                c_void_p], c_int),
+                               c_void_p], c_int),
     "fmd_filter_cfconv_bwd": ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
                               c_int),
-    "fmd_filter_cfconv_bwd2": ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
-                               c_int),
-    "fmd_debug_set_trace": ([c_void_p], c_int),
+    "fmd_debug_set_trace_fwd": ([c_void_p], c_int),
+    "fmd_debug_set_trace_bwd": ([c_void_p], c_int),
     "fmd_linear": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                     c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "fmd_linear_tc": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
@@ -85,7 +80,6 @@ _SIGS = {
                         c_void_p], c_int),
     "fmd_baoab_pre": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p,
                        c_int, c_float, c_float, c_float, c_void_p], c_int),
-    "fmd_l2_prefetch": ([c_void_p, c_uint64, c_void_p], c_int),
     "fmd_increment_u64": ([c_void_p, c_void_p], c_int),
     "fmd_baoab_post": ([c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "fmd_philox_normal": ([c_uint64, c_uint64, c_int, c_void_p, c_void_p], c_int),

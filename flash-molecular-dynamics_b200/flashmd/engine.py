@@ -83,6 +83,7 @@ class SchNetWeights:
                 wp[:, :self.num_rbf] = k[f"b{l}.f0_w.h"]
                 k[f"b{l}.f0_w.hp"] = wp.contiguous()
         k["emb_lin1"] = (k["embedding"].double() @ k["b0.lin1_w"].double().t()).float().contiguous()
+        k["emb_lin1.h"] = k["emb_lin1"].half().contiguous()
         self.k = k
         # [K,N] weight tensor -> the same matrix stored [N,K] (its transpose twin), for fmd_linear_tc's fast staging
         self.twin = {}
@@ -234,7 +235,8 @@ class ForceField:
         wdt = torch.float16 if precision == "w16a16" else f32
         # W16A16 with the default widths runs the fused tcgen05 kernels (no [E,F] tensor in HBM);
         # other widths / the fp32 parity path use the materialised SIMT kernels.
-        self.fused_tc = (precision == "w16a16" and F == 128 and H == 128 and R <= 64 and use_tensor_cores)
+        # (num_rbf <= 63: one padded column of the radial-basis operand carries the bias through the first GEMM)
+        self.fused_tc = (precision == "w16a16" and F == 128 and H == 128 and R <= 63 and use_tensor_cores)
         # fp32 parity path: dense layers as fp32-accurate BF16x3 (fp32-emulation) tensor-core GEMMs (fmd_linear_x3) instead of SIMT FMA
         self.x3 = precision == "fp32" and use_tensor_cores and os.environ.get("FMD_X3", "1") == "1"
         # node-level layers stay on the true-fp32 FMA kernel by default: they are 6 % of the step and the tensor-core
@@ -260,12 +262,15 @@ class ForceField:
             self.g_rbf = torch.zeros((cap, R), dtype=f32, device=dev)
         self.g_d = torch.zeros(cap, dtype=f32, device=dev)
         self.h = [torch.zeros((N, H), dtype=f32, device=dev) for _ in range(nb + 1)]
-        self.a = [torch.zeros((N, F), dtype=f32, device=dev) for _ in range(nb)]
+        # the operands the fused edge kernels gather per edge (a, g_m) are stored as fp16 rows: half the L2 traffic of the
+        # gathers, 16-byte cp.async staging (the reference multiplies fp32 x by the fp16 filter: ours rounds x as well)
+        gdt = torch.float16 if self.fused_tc else f32
+        self.a = [torch.zeros((N, F), dtype=gdt, device=dev) for _ in range(nb)]
         self.m = torch.zeros((N, F), dtype=f32, device=dev)
         self.c = [torch.zeros((N, H), dtype=f32, device=dev) for _ in range(nb)]
         self.g_h = [torch.zeros((N, H), dtype=f32, device=dev) for _ in range(2)]
         self.g_c = torch.zeros((N, H), dtype=f32, device=dev)
-        self.g_m = torch.zeros((N, F), dtype=f32, device=dev)
+        self.g_m = torch.zeros((N, F), dtype=gdt, device=dev)
         self.g_a = torch.zeros((N, F), dtype=f32, device=dev)
         odt = torch.float16 if precision == "w16a16" else f32
         widths = [weights.tensors[f"out{i}_w"].shape[0] for i in range(weights.num_out_layers)]
@@ -322,9 +327,11 @@ class ForceField:
         self._n += 1
 
     def _filter_cfconv(self, l, x, out):
-        """out[i] = sum_{e in seg(i)} W_l(d_e) * x[dst_e] * C(d_e): filter network + CFConv fused on tensor cores."""
+        """out[i] = sum_{e in seg(i)} W_l(d_e) * x[dst_e] * C(d_e): filter network + CFConv fused on tensor cores
+        (x: fp16 [N,128])."""
+        assert x.dtype == torch.float16
         w, k = self.w, self.w.k
-        L.call("fmd_filter_cfconv_fwd2", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.seg_ptr), self.N,
+        L.call("fmd_filter_cfconv_fwd", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.seg_ptr), self.N,
                self.cap, L.ptr(self.n_edges_dev), L.ptr(k[f"b{l}.f0_w.hp"]), L.ptr(k[f"b{l}.f0_b.h"]),
                L.ptr(k[f"b{l}.f1_w.h"]), L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(x), w.filters,
                L.ptr(out), L.ptr(self.part), self._st)
@@ -333,7 +340,7 @@ class ForceField:
     def _filter_cfconv_bwd(self, l, a, g_m):
         """g_d[e] += d/dd_e of sum_f g_m[src_e,f] W_l(d_e)[f] a[dst_e,f] C(d_e) (fused, tensor cores)."""
         w, k = self.w, self.w.k
-        L.call("fmd_filter_cfconv_bwd2", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), self.cap,
+        L.call("fmd_filter_cfconv_bwd", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), self.cap,
                L.ptr(self.n_edges_dev), L.ptr(k[f"b{l}.f0_w.hp"]), L.ptr(k[f"b{l}.f0_b.h"]), L.ptr(k[f"b{l}.f1_w.h"]),
                L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(a), L.ptr(g_m), w.filters, L.ptr(self.g_d), 1,
                int(self.exact), self._st)
@@ -372,7 +379,8 @@ class ForceField:
         T, TC = L.ACT_TANH, L.ACT_TANH_CLAMPED
         self.build_neighbor_list(pos)
         L.call("fmd_embedding", L.ptr(k["embedding"]), L.ptr(self.types), 4, self.N, w.hidden, L.ptr(self.h[0]), st)
-        L.call("fmd_embedding", L.ptr(k["emb_lin1"]), L.ptr(self.types), 4, self.N, w.filters, L.ptr(self.a[0]), st)
+        # a_0 = (Emb W1^T)[types] as fp16 rows (256 B = 64 floats for the row-copy kernel)
+        L.call("fmd_embedding", L.ptr(k["emb_lin1.h"]), L.ptr(self.types), 4, self.N, w.filters // 2, L.ptr(self.a[0]), st)
         self._n += 2
         for l in range(nb):
             self._filter_cfconv(l, self.a[l], self.m)
@@ -432,7 +440,10 @@ class ForceField:
         for l in range(nb):
             if l == 0:
                 # a_0 = Emb[types] W1^T = (Emb W1^T)[types]: the [n_types, F] product is precomputed once
-                L.call("fmd_embedding", L.ptr(k["emb_lin1"]), L.ptr(self.types), 4, self.N, w.filters, L.ptr(self.a[0]), st)
+                if tc:
+                    L.call("fmd_embedding", L.ptr(k["emb_lin1.h"]), L.ptr(self.types), 4, self.N, w.filters // 2, L.ptr(self.a[0]), st)
+                else:
+                    L.call("fmd_embedding", L.ptr(k["emb_lin1"]), L.ptr(self.types), 4, self.N, w.filters, L.ptr(self.a[0]), st)
                 self._n += 1
             else:
                 self._lin(self.h[l], k[f"b{l}.lin1_wT"], None, self.a[l])

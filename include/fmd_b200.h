@@ -147,22 +147,18 @@ int fmd_cfconv_grad_filter(const float* x, const float* g_out, const float* dist
  *   out[i,:] = sum_{e in [seg_ptr[i], seg_ptr[i+1])} (tanh(rbf_e Wf0^T + bf0) Wf1^T) * x[edge_nbr[e],:] * C(dist[e])
  * Edge list: the sorted symmetric list of fmd_nl_fill (edge_owner = its edge_src, edge_nbr = its edge_dst,
  * int32). wf0_h [128,64] fp16 = Wf0 [out,in] zero-padded from num_rbf to 64 columns; bf0_h [128] fp16 or
- * NULL; wf1_h [128,128] fp16 [out,in]. n_feat must be 128, num_rbf <= 64. x, out [n_nodes,128] f32.
- * part: scratch, >= ceil(capacity/128)*128 floats. dbg_t / dbg_w (nullable): dump t and W as [E,128] fp16.
- * Deterministic, atomic-free. */
+ * NULL; wf1_h [128,128] fp16 [out,in]. n_feat must be 128, num_rbf <= 63 (one padded column of the radial-basis
+ * operand is a constant 1 that carries the bias through the first GEMM).
+ * x_h [n_nodes,128] fp16: the gathered operand; its rows are staged through shared memory with cp.async (every epilogue
+ * warp prefetches its own 64-byte feature slice one tile ahead). The filter value is rounded to fp16 like the
+ * reference's [E,F] fp16 filter tensor and multiplied with one mixed-precision FMA per element (fp32 accumulate).
+ * out [n_nodes,128] f32. part: scratch, >= ceil(capacity/128)*128 floats. Deterministic, atomic-free.
+ * One persistent CTA per SM, producer / MMA-issuer / tanh / epilogue warps connected by mbarrier rings, D1 and D2
+ * double-buffered in TMEM (512 columns). */
 int fmd_filter_cfconv_fwd(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr,
                           const int32_t* seg_ptr, int n_nodes, int capacity, const int32_t* n_edges_dev,
                           const void* wf0_h, const void* bf0_h, const void* wf1_h, const float* centers, int num_rbf,
-                          float gamma, float rc, const float* x, int n_feat, float* out, float* part, void* dbg_t,
-                          void* dbg_w, void* stream);
-
-/* Same contract as fmd_filter_cfconv_fwd (without the debug dumps): the warp-specialised, software-pipelined
- * kernel used on the step path - one persistent CTA per SM, producer / MMA-issuer / tanh / epilogue warps
- * connected by mbarrier rings, D1 and D2 double-buffered in TMEM (512 columns). */
-int fmd_filter_cfconv_fwd2(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr,
-                           const int32_t* seg_ptr, int n_nodes, int capacity, const int32_t* n_edges_dev,
-                           const void* wf0_h, const void* bf0_h, const void* wf1_h, const float* centers, int num_rbf,
-                           float gamma, float rc, const float* x, int n_feat, float* out, float* part, void* stream);
+                          float gamma, float rc, const void* x_h, int n_feat, float* out, float* part, void* stream);
 
 /* replaces, for the W16A16 path, the edge part of FusedCSRCFConvFunction.backward + the filter network's
  * backward + the fused-RBF backward: fused_grad_filter_out (kernels/cfconv_kernels.py:178-337),
@@ -172,23 +168,20 @@ int fmd_filter_cfconv_fwd2(const float* dist, const int32_t* edge_owner, const i
  * through the radial basis (always) and through C (only when exact_cutoff_grad != 0; 0 reproduces the
  * reference's Triton backward, kernels/csr_kernels.py:912). t is recomputed on the tensor cores, g_W, g_t
  * are fp16 tensor-core operands (as in the reference) and never reach HBM. Same edge list / weight
- * layout as fmd_filter_cfconv_fwd. a, g_m [n_nodes,128] f32. */
+ * layout as fmd_filter_cfconv_fwd. a_h, g_m_h [n_nodes,128] fp16: the rows a[edge_nbr[e],:] are copied by cp.async
+ * straight into the swizzled K-major operand buffer of the g_W GEMM, one tile ahead, and multiplied in place by
+ * g_m[edge_owner[e],:] with packed fp16 arithmetic. */
 int fmd_filter_cfconv_bwd(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr, int capacity,
                           const int32_t* n_edges_dev, const void* wf0_h, const void* bf0_h, const void* wf1_h,
-                          const float* centers, int num_rbf, float gamma, float rc, const float* a, const float* g_m,
+                          const float* centers, int num_rbf, float gamma, float rc, const void* a_h, const void* g_m_h,
                           int n_feat, float* g_d, int accumulate, int exact_cutoff_grad, void* stream);
 
-/* Same contract as fmd_filter_cfconv_bwd: the warp-specialised, software-pipelined kernel used on the step
- * path (producer+g_d / gather / tanh+g_t / MMA-issuer warps, mbarrier rings, D1|D3 and D4 double-buffered in TMEM). */
-int fmd_filter_cfconv_bwd2(const float* dist, const int32_t* edge_owner, const int32_t* edge_nbr, int capacity,
-                           const int32_t* n_edges_dev, const void* wf0_h, const void* bf0_h, const void* wf1_h,
-                           const float* centers, int num_rbf, float gamma, float rc, const float* a, const float* g_m,
-                           int n_feat, float* g_d, int accumulate, int exact_cutoff_grad, void* stream);
-
-/* tools only (scripts/trace_roles.py): when device_buffer != NULL, CTA 0 of the pipelined tensor-core kernels
- * records clock64() stamps {wait start, work start, end} per warp role and tile into
- * uint64 trace[9 roles][64 tiles][3]; NULL switches the trace off. Not used on the step path. */
-int fmd_debug_set_trace(void* device_buffer);
+/* tools only (scripts/trace_roles.py): when device_buffer != NULL, the next launches of the forward / backward fused
+ * kernel run a traced instantiation in which CTA 0 records clock64() stamps {wait start, work start, end} per warp role
+ * and tile into uint64 trace[9 roles][64 tiles][3]; NULL switches back to the production instantiation (which contains
+ * no trace code). */
+int fmd_debug_set_trace_fwd(void* device_buffer);
+int fmd_debug_set_trace_bwd(void* device_buffer);
 
 /* ---------------------------------------------------------------- dense layers -------------- */
 
@@ -319,11 +312,6 @@ int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair_ptr, const
 int fmd_baoab_pre(float* pos, float* vel, const float* forces, const float* inv_mass, const float* noise_std,
                   const float* noise, uint64_t seed, uint64_t step, const uint64_t* step_dev, int n_nodes,
                   float dt, float vscale, float noisescale, void* stream);
-
-/* Issues prefetch.global.L2 for [ptr, ptr+bytes): warms the 126 MB L2 with a node-feature matrix that a later
- * edge kernel gathers row-wise (first touches would otherwise pay DRAM latency inside a latency-bound loop).
- * Part of the fused step only; no reference counterpart. */
-int fmd_l2_prefetch(const void* ptr, uint64_t bytes, void* stream);
 
 /* *counter += 1 on the stream (keeps the Philox step counter on the device so a captured CUDA
  * graph of the whole step can be replayed; fmd_baoab_pre adds *step_dev to `step`). */

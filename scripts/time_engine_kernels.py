@@ -28,10 +28,10 @@ for exact in (True, False):
         for _ in range(reps): fn()
         b.record(); torch.cuda.synchronize(); return a.elapsed_time(b)/reps
     print("exact",exact,"edges",ff.num_edges(),"cap",ff.cap,
-          "fwd2 %.4f ms"%t(lambda: ff._filter_cfconv(1,ff.a[1],ff.m)),
-          "bwd2 %.4f ms"%t(lambda: ff._filter_cfconv_bwd(1,ff.a[1],ff.g_m)),
-          "bwd2 with randn g_m %.4f ms"%t(lambda: ff._filter_cfconv_bwd(1,ff.a[1],torch.randn_like(ff.g_m)) if False else ff._filter_cfconv_bwd(1,ff.a[1],ff.g_m)))
-    gm=ff.g_m; print("  |g_m| mean %.3e  |a| mean %.3e"%(gm.abs().mean().item(), ff.a[1].abs().mean().item()))
-    gr=torch.randn_like(gm)
-    print("  bwd2 randn g_m %.4f ms"%t(lambda: ff._filter_cfconv_bwd(1,ff.a[1],gr)))
+          "fwd %.4f ms"%t(lambda: ff._filter_cfconv(1,ff.a[1],ff.m)),
+          "bwd %.4f ms"%t(lambda: ff._filter_cfconv_bwd(1,ff.a[1],ff.g_m)),
+          "bwd again %.4f ms"%t(lambda: ff._filter_cfconv_bwd(1,ff.a[1],torch.randn_like(ff.g_m)) if False else ff._filter_cfconv_bwd(1,ff.a[1],ff.g_m)))
+    gm=ff.g_m; print("  |g_m| mean %.3e  |a| mean %.3e"%(gm.float().abs().mean().item(), ff.a[1].float().abs().mean().item()))
+    gr=torch.randn(gm.shape,device=gm.device).to(gm.dtype)
+    print("  bwd randn g_m %.4f ms"%t(lambda: ff._filter_cfconv_bwd(1,ff.a[1],gr)))
     # capacity == exact edge count (no slack tiles)

@@ -1,48 +1,20 @@
-"""Role timeline of the pipelined backward kernel (GPU box): per tile, cycles each role spent waiting / working."""
-import os, sys
-import numpy as np
+"""Tools (GPU box): the fused backward kernel on the bench's engine state - determinism, time per call (exact and
+Triton-compatible cut-off gradient), and the role timeline of CTA 0 (traced instantiation of the kernel)."""
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "flash-molecular-dynamics_b200"))
-from flashmd import _lib as L
-from flashmd.neighbor_list.torch_impl import radius_graph_csr
-L.load()
-dev = "cuda"
-rng = np.random.default_rng(0)
-sizes = [269] * 128
-pos = torch.from_numpy(np.concatenate([rng.uniform(0, 24.0, size=(s, 3)) for s in sizes]).astype(np.float32)).to(dev)
-ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)])).to(dev)
-rc, R, F = 10.5, 50, 128
-g = radius_graph_csr(pos, ptr, rc, idx_dtype=torch.int32)
-src, dst, dist = g["edge_index"][0].contiguous(), g["edge_index"][1].contiguous(), g["dist"]
-E, N = src.numel(), pos.shape[0]
-gen = torch.Generator().manual_seed(0)
-wf0p = torch.zeros((F, 64), dtype=torch.float16); wf0p[:, :R] = (torch.rand((F, R), generator=gen) - 0.5).half()
-wf0p = wf0p.to(dev); bf0h = torch.zeros(F, dtype=torch.float16, device=dev)
-wf1h = ((torch.rand((F, F), generator=gen) - 0.5) * 0.3).half().to(dev)
-a = torch.randn((N, F), generator=gen).to(dev); gm = torch.randn((N, F), generator=gen).to(dev)
-centers = torch.linspace(0, rc, R).to(dev); gamma = float(-0.5 / (centers[1] - centers[0]) ** 2)
-g_d = torch.zeros(E, device=dev)
-trace = torch.zeros(9 * 64 * 3, dtype=torch.int64, device=dev)
-def run():
-    L.call("fmd_filter_cfconv_bwd2", L.ptr(dist), L.ptr(src), L.ptr(dst), E, None, L.ptr(wf0p), L.ptr(bf0h), L.ptr(wf1h),
-           L.ptr(centers), R, gamma, rc, L.ptr(a), L.ptr(gm), F, L.ptr(g_d), 1, 1, L.stream_ptr())
-for _ in range(3): run()
-L.call("fmd_debug_set_trace", L.ptr(trace)); run(); torch.cuda.synchronize(); L.call("fmd_debug_set_trace", None)
-t = trace.cpu().numpy().reshape(9, 64, 3).astype(np.int64)
-t0 = t[t > 0].min()
-names = ["produce", "e4", "G0", "G1", "T-A", "T-B", "M1", "M3", "M4"]
-print("per-role mean cycles over tiles 8..40:  wait / work   (tile period from produce ends)")
-for r, nm in enumerate(names):
-    rows = [i for i in range(8, 40) if t[r, i, 0] > 0 and t[r, i, 1] > 0]
-    if not rows: continue
-    if nm == "M3":
-        w = np.mean([t[r, i, 1] - t[r, i, 0] for i in rows]); print(f"{nm:8s} wait {w:8.0f}  (of which GW_FULL {np.mean([t[r,i,2]-t[r,i,0] for i in rows]):8.0f})")
-    elif nm.startswith("M"):
-        print(f"{nm:8s} wait {np.mean([t[r, i, 1] - t[r, i, 0] for i in rows]):8.0f}")
-    else:
-        print(f"{nm:8s} wait {np.mean([t[r, i, 1] - t[r, i, 0] for i in rows]):8.0f}  work {np.mean([t[r, i, 2] - t[r, i, 1] for i in rows]):8.0f}")
-pe = t[0, 8:40, 2]; print("tile period (cycles):", np.mean(np.diff(pe)))
-print("timeline of tiles 10..13 (cycles since first stamp): role: wait_start work_start end")
-for i in range(10, 14):
-    print(f" tile {i}: " + "  ".join(f"{names[r]}:{t[r,i,0]-t0}/{t[r,i,1]-t0}/{t[r,i,2]-t0}" for r in range(9) if t[r, i, 0] > 0))
+from _bench_state import L, engine_state, print_timeline, time_ms
+for exact in (1, 0):
+    ff, w = engine_state(exact=bool(exact))
+    k, l = w.k, 1
+    ah, gh = ff.a[l], ff.g_m
+    gd = torch.zeros_like(ff.g_d)
+    def bwd():
+        L.call("fmd_filter_cfconv_bwd", L.ptr(ff.dist), L.ptr(ff.src), L.ptr(ff.dst), ff.cap, L.ptr(ff.n_edges_dev), L.ptr(k[f"b{l}.f0_w.hp"]),
+               L.ptr(k[f"b{l}.f0_b.h"]), L.ptr(k[f"b{l}.f1_w.h"]), L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(ah), L.ptr(gh),
+               w.filters, L.ptr(gd), 0, exact, ff._st)
+    bwd(); torch.cuda.synchronize()
+    g1 = gd.clone(); bwd(); torch.cuda.synchronize()
+    print("exact", exact, "edges", ff.num_edges(), "deterministic:", torch.equal(gd, g1), "finite:", bool(torch.isfinite(gd).all()),
+          "backward %.4f ms per call" % time_ms(bwd))
+trace = torch.zeros(9 * 64 * 3, dtype=torch.int64, device="cuda")
+L.call("fmd_debug_set_trace_bwd", L.ptr(trace)); bwd(); torch.cuda.synchronize(); L.call("fmd_debug_set_trace_bwd", None)
+print_timeline(trace, ["P", "E4", "G", "-", "A", "B", "M1", "M3", "M4"])
