@@ -41,6 +41,13 @@ def parse():
     ap.add_argument("--batch", type=int, default=128, help="molecules per GPU")
     ap.add_argument("--blocks", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-triton-baseline", action="store_true",
+                    help="skip the reference's Triton GPU path (timed on the same GPU after our own run, N = 1 only)")
+    ap.add_argument("--min-seconds", type=float, default=0.5,
+                    help="the timed region replays the K-step block until it is at least this long (per-step numbers divide back)")
+    ap.add_argument("--pt", action="store_true",
+                    help="BASELINE config 4: parallel tempering, betas [1.67, 1.42, 1.16] x 256 replicas (768 simulations "
+                         "sharded over the ranks), replica exchange every 100 steps (NCCL energy all-gather + peer swaps)")
     ap.add_argument("--profile-kernels", action="store_true", help="print per-kernel event timings to stderr")
     return ap.parse_args()
 
@@ -271,7 +278,9 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("FMD_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL's own log (communicator size, NVLS / ring choice) is kept, but away from stdout (one JSON line there)
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -279,7 +288,10 @@ def main():
     from flashmd.engine import (ForceField, LangevinEngine, SchNetWeights, prior_terms_from_system,
                                 random_schnet_tensors)
     L.load()
-    sysd, pos_np = build_system(args, seed=rank)
+    if args.pt:
+        return run_pt(args, rank, world, local, dev, dist)
+    # the SAME molecules on every rank (weak scaling with identical work per GPU); velocities and noise differ per rank
+    sysd, pos_np = build_system(args, seed=0)
     B, n = args.batch, args.n_beads
     pos = torch.from_numpy(pos_np).reshape(B * n, 3).to(dev).contiguous()
     types = torch.from_numpy(sysd["atom_types"]).repeat(B).to(dev)
@@ -294,7 +306,8 @@ def main():
     masses = torch.from_numpy(sysd["masses"]).repeat(B)
     g = torch.Generator().manual_seed(1234 + rank)
     v0 = torch.randn((B * n, 3), generator=g) * torch.sqrt(1.0 / (BETA * masses))[:, None]
-    eng = LangevinEngine(ff, pos, v0, masses, torch.full((B,), BETA), DT, FRICTION, seed=SEED + rank, use_graph=True)
+    eng = LangevinEngine(ff, pos, v0, masses, torch.full((B,), BETA), DT, FRICTION, seed=SEED, use_graph=True,
+                         node_offset=rank * B * n)     # Philox noise keyed by the global bead index
 
     def barrier():
         if dist is not None:
@@ -304,6 +317,20 @@ def main():
     # ---- device-resident timing (value)
     for _ in range(max(args.warmup, 3)):
         eng.step()
+    edges_start = ff.num_edges()
+    # the timed region is `repeats` back-to-back blocks of exactly K steps, long enough (--min-seconds) that launch jitter
+    # and the barrier do not show in the max-over-ranks time; per-step numbers divide back
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.step()
+    torch.cuda.synchronize()
+    est = (time.perf_counter() - t0) / 3
+    repeats = max(1, int(np.ceil(args.min_seconds / max(est * args.steps, 1e-9))))
+    if dist is not None:
+        rt = torch.tensor([repeats], device=dev)
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        repeats = int(rt.item())
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -311,20 +338,28 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(repeats * args.steps):
         eng.step()
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms_rank = ev0.elapsed_time(ev1)
+    ms = ms_rank
     clocks = sampler.stop() if rank == 0 else None
+    edges_now = ff.num_edges()
+    per_rank = {"ms_per_step": [ms_rank / (repeats * args.steps)], "edges_start": [edges_start], "edges_end": [edges_now]}
     if dist is not None:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    edges_now = ff.num_edges()
+        mine = torch.tensor([ms_rank / (repeats * args.steps), float(edges_start), float(edges_now)], device=dev, dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [float(a[0]) for a in allr], "edges_start": [int(a[1]) for a in allr],
+                    "edges_end": [int(a[2]) for a in allr]}
     assert edges_now <= cap, f"edge capacity overflow: {edges_now} > {cap}"
     assert torch.isfinite(eng.pos).all(), "trajectory diverged"
-    value = world * B * args.steps / (ms * 1e-3)
+    n_timed = repeats * args.steps
+    value = world * B * n_timed / (ms * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers (H2D + step + D2H inside the timed region)
     ph = torch.empty((B * n, 3), dtype=torch.float32).pin_memory()
@@ -355,7 +390,8 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / n_timed, "higher_is_better": True,
+            "timed_steps": n_timed, "repeats_of_k_steps": repeats,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 filter-network operands / tf32 node layers / f32 accumulate" if args.precision == "w16a16" else "f32",
             "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
@@ -363,12 +399,157 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": eng.launches_per_step * args.steps,
             "launches_per_step": eng.launches_per_step,
-            "edges": edges_now, "nodes": B * n,
+            "edges": edges_now, "edges_start": edges_start, "nodes": B * n,
+            "per_rank": per_rank,
             "roofline": roof, "kernels_ms_per_step": kern_table,
         }
+        if dist is not None:
+            line["nccl"] = {"nranks": world, "version": ".".join(str(v) for v in torch.cuda.nccl.version()),
+                            "data_path_collectives_per_step": 0, "log": os.environ.get("NCCL_DEBUG_FILE")}
+        if world == 1 and not args.no_triton_baseline and args.precision == "w16a16" and args.blocks == 3:
+            line["triton_baseline"] = triton_baseline_entry(args, value)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_entry(args, 16, 8)[0]
         print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def triton_baseline_entry(args, our_value):
+    """The UNMODIFIED reference's default GPU path (Triton kernels, gptq="w16a16", all MLCG_*=1) timed on the SAME GPU and
+    the same synthetic workload right after our own run, in a subprocess (its package name clashes with the drop-in):
+    scripts/bench_triton_reference.py, the reference's own second-half throughput metric (simulation/base.py:748-787).
+    compile_model=True (the reference's default, simulation/base.py:362-368) is tried first; with torch 2.11 + triton 3.6
+    inductor rejects the reference's own CSR kernel, so the error is recorded and the eager run is the baseline."""
+    script = os.path.join(ROOT, "scripts", "bench_triton_reference.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "flashmd")):
+        return {"unavailable": "baseline/_ref (pip install --target of the reference) is absent"}
+    env = dict(os.environ, CXX=os.environ.get("FMD_REF_CXX", "/usr/bin/g++"))    # the image's default g++ wrapper lacks libgomp.spec
+    out = {"nl": "radius_graph served by this repo's CUDA kernel (torch_cluster is not installable)", "steps": 100}
+
+    def run(compile_flag, timeout):
+        cmd = [sys.executable, script, "--device", "cuda", "--batch", str(args.batch), "--n-beads", str(args.n_beads),
+               "--steps", "100", "--gptq", "w16a16", "--compile", str(compile_flag)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        recs = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not recs:
+            errs = [ln for ln in (r.stderr or "").splitlines() if "Error" in ln or "error" in ln]
+            return None, (errs[-1] if errs else (r.stderr or "")[-300:]).strip()[:400]
+        return json.loads(recs[-1]), None
+    try:
+        rec, err = (None, "skipped (FMD_REF_COMPILE=0)") if os.environ.get("FMD_REF_COMPILE", "1") == "0" else run(1, 600)
+        out["compile_model"] = rec is not None
+        if rec is None:
+            out["compile_model_error"] = err
+            rec, err = run(0, 600)
+        if rec is None:
+            out["unavailable"] = err
+            return out
+        m = rec["metrics"]
+        out.update({"value": float(m["throughput"]), "unit": UNIT, "ms_per_step": float(m["ms_per_timestep"]),
+                    "second_half_steps": int(m["second_half_steps"]), "attach_s": rec.get("attach_s"),
+                    "ours_over_triton": our_value / float(m["throughput"]), "notes": rec.get("notes")})
+    except Exception as e:  # noqa: BLE001
+        out["unavailable"] = repr(e)[:300]
+    return out
+
+
+def run_pt(args, rank, world, local, dev, dist):
+    """BASELINE config 4 on the fused engine: 3 betas x 256 replicas = 768 simulations of the 269-bead molecule sharded
+    contiguously over the ranks (reference layout: sim = beta_index * n_indep + replica), Langevin steps replayed as a
+    CUDA graph, replica exchange every 100 steps (simulation/distributed.py: NCCL all-gather of the energies, device-side
+    decisions, static peer exchange).  One "step" = one BAOAB step of all 768 simulations; strong scaling."""
+    from flashmd import _lib as L
+    from flashmd.engine import ForceField, LangevinEngine, SchNetWeights, prior_terms_from_system, random_schnet_tensors
+    from flashmd.neighbor_list import radius_graph_csr
+    from flashmd.simulation.distributed import ShardedExchange, shard_range
+    from flashmd.simulation.parallel_tempering import adjacent_pairs
+    L.load()
+    betas, n_indep, interval = [1.67, 1.42, 1.16], 256, 100
+    n_total = len(betas) * n_indep
+    lo, hi = shard_range(n_total, rank, world)
+    B, n = hi - lo, args.n_beads
+    from flashmd import synthetic
+    sysd = synthetic.synthetic_system(16, n, seed=0)
+    pos_np = np.stack([sysd["pos"][(s % n_indep) % 16] for s in range(lo, hi)])
+    beta_all = torch.tensor([b for b in betas for _ in range(n_indep)], dtype=torch.float32)
+    pos = torch.from_numpy(pos_np).reshape(B * n, 3).to(dev).contiguous()
+    types = torch.from_numpy(sysd["atom_types"]).repeat(B).to(dev)
+    mol_ptr = (torch.arange(B + 1) * n).to(dev)
+    w = SchNetWeights.from_flat(random_schnet_tensors(0, num_blocks=args.blocks), sysd["cutoff"], 50, dev)
+    priors = prior_terms_from_system(sysd, B, dev)
+    e0 = radius_graph_csr(pos, mol_ptr, sysd["cutoff"], idx_dtype=torch.int32)["edge_index"].shape[1]
+    cap = int(1.35 * e0) + 4096
+    ff = ForceField(w, priors, types, mol_ptr, precision=args.precision, edge_capacity=cap)
+    masses = torch.from_numpy(sysd["masses"]).repeat(B)
+    beta_loc = beta_all[lo:hi]
+    g = torch.Generator().manual_seed(1234 + rank)
+    v0 = torch.randn((B * n, 3), generator=g) * torch.sqrt(1.0 / (beta_loc.repeat_interleave(n) * masses))[:, None]
+    eng = LangevinEngine(ff, pos, v0, masses, beta_loc, DT, FRICTION, seed=SEED, use_graph=True, node_offset=lo * n)
+    ex = ShardedExchange(beta_all, n, rank, world)
+    even, odd = adjacent_pairs(len(betas), n_indep)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    accs = []
+
+    def block(k):
+        for _ in range(interval):
+            eng.step()
+        pa, pb = even if k % 2 == 0 else odd
+        accs.append(ex.exchange(eng.pos, eng.vel, ff.energy, pa, pb, None, SEED, k))   # counter-based decisions on the device
+
+    for k in range(2):
+        block(k)
+    edges_start = ff.num_edges()
+    n_blocks = max(1, -(-max(args.steps, interval) // interval))
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(2, 2 + n_blocks):
+        block(k)
+    ev1.record()
+    barrier()
+    ms_rank = ev0.elapsed_time(ev1)
+    ms = ms_rank
+    clocks = sampler.stop() if rank == 0 else None
+    edges_now = ff.num_edges()
+    steps = n_blocks * interval
+    per_rank = {"ms_per_step": [ms_rank / steps], "edges_start": [edges_start], "edges_end": [edges_now]}
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        mine = torch.tensor([ms_rank / steps, float(edges_start), float(edges_now)], device=dev, dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [float(a[0]) for a in allr], "edges_start": [int(a[1]) for a in allr],
+                    "edges_end": [int(a[2]) for a in allr]}
+    assert edges_now <= cap and torch.isfinite(eng.pos).all()
+    n_acc = int(sum(int(a.sum()) for a in accs[2:]))
+    if rank == 0:
+        cfg = workload_config(args, world)
+        cfg.update({"workload": f"parallel tempering (BASELINE config 4): betas {betas} x {n_indep} replicas = {n_total} simulations "
+                                f"of the {n}-bead molecule, exchange every {interval} steps, sharded over {world} GPU(s)",
+                    "batch_per_gpu": B, "global_batch": n_total,
+                    "parallelism": f"replicas sharded x{world}; per exchange: NCCL all-gather of {n_total} energies + static peer swap"})
+        print(json.dumps({
+            "metric": METRIC.replace("batch128 Langevin", "parallel tempering 3x256"), "value": n_total * steps / (ms * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": 2 * interval, "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16 filter-network operands / tf32 node layers / f32 accumulate", "data": "synthetic", "config": cfg,
+            "clocks": clocks, "gpu_launches": eng.launches_per_step * steps, "launches_per_step": eng.launches_per_step,
+            "edges": edges_now, "edges_start": edges_start, "nodes": B * n, "per_rank": per_rank,
+            "exchanges": {"n": n_blocks, "pairs_proposed": int(sum(a.numel() for a in accs[2:])), "pairs_accepted": n_acc,
+                          "rng": "Philox keyed by (seed, exchange index, pair), identical on every rank"},
+            "nccl": None if dist is None else {"nranks": world, "version": ".".join(str(v) for v in torch.cuda.nccl.version())}}))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256)
 baoab_pre_kernel(float* __restrict__ pos, float* __restrict__ vel, const float* __restrict__ forces,
                  const float* __restrict__ inv_mass, const float* __restrict__ noise_std,
                  const float* __restrict__ noise, uint64_t seed, uint64_t step, const uint64_t* __restrict__ step_dev,
-                 int n_nodes, float dt, float vscale, float noisescale) {
+                 uint64_t node_offset, int n_nodes, float dt, float vscale, float noisescale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes) return;
   if (step_dev) step += *step_dev;
@@ -172,7 +172,7 @@ baoab_pre_kernel(float* __restrict__ pos, float* __restrict__ vel, const float* 
   if (noise) {
     z[0] = noise[3 * i]; z[1] = noise[3 * i + 1]; z[2] = noise[3 * i + 2];
   } else {
-    normal3(seed, step, (uint64_t)i, z[0], z[1], z[2]);
+    normal3(seed, step, node_offset + (uint64_t)i, z[0], z[1], z[2]);
   }
   const float im = inv_mass[i], ns = noise_std[i];
   const float hdt = 0.5f * dt;
@@ -357,12 +357,12 @@ extern "C" int fmd_increment_u64(uint64_t* counter, void* stream) {
 }
 
 extern "C" int fmd_baoab_pre(float* pos, float* vel, const float* forces, const float* inv_mass, const float* noise_std,
-                             const float* noise, uint64_t seed, uint64_t step, const uint64_t* step_dev, int n_nodes,
+                             const float* noise, uint64_t seed, uint64_t step, const uint64_t* step_dev, uint64_t node_offset, int n_nodes,
                              float dt, float vscale, float noisescale, void* stream) {
   FMD_REQUIRE(pos && vel && forces && inv_mass && noise_std, "fmd_baoab_pre: bad arguments");
   if (n_nodes == 0) return FMD_OK;
   baoab_pre_kernel<<<fmd_div_up(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(pos, vel, forces, inv_mass, noise_std,
-                                                                                noise, seed, step, step_dev, n_nodes, dt,
+                                                                                noise, seed, step, step_dev, node_offset, n_nodes, dt,
                                                                                 vscale, noisescale);
   FMD_CHECK_LAUNCH();
   return FMD_OK;

@@ -79,7 +79,7 @@ _SIGS = {
                         c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                         c_void_p], c_int),
     "fmd_baoab_pre": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p,
-                       c_int, c_float, c_float, c_float, c_void_p], c_int),
+                       c_uint64, c_int, c_float, c_float, c_float, c_void_p], c_int),
     "fmd_increment_u64": ([c_void_p, c_void_p], c_int),
     "fmd_baoab_post": ([c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "fmd_philox_normal": ([c_uint64, c_uint64, c_int, c_void_p, c_void_p], c_int),

@@ -53,6 +53,8 @@ class SchNetWeights:
     cutoff: float
     num_rbf: int
     rbf_lower: float = 0.0
+    rbf_centers: Optional[torch.Tensor] = None     # trained / non-default basis: explicit centres and coefficient
+    rbf_gamma: Optional[float] = None
 
     def __post_init__(self):
         t = self.tensors
@@ -63,6 +65,11 @@ class SchNetWeights:
         # RBF parameters exactly as GaussianBasis._initial_params (reference radial_basis/gaussian.py:64-75)
         centers = torch.linspace(self.rbf_lower, self.cutoff, self.num_rbf)
         self.gamma = float(-0.5 / (centers[1] - centers[0]) ** 2)
+        if self.rbf_centers is not None:
+            centers = self.rbf_centers.detach().float().cpu().flatten()
+            assert centers.numel() == self.num_rbf
+        if self.rbf_gamma is not None:
+            self.gamma = float(self.rbf_gamma)
         self.centers = centers.to(dev).float().contiguous()
         k: Dict[str, torch.Tensor] = {}
         for name, w in t.items():
@@ -95,11 +102,12 @@ class SchNetWeights:
         self.ones_col = None
 
     @staticmethod
-    def from_flat(tensors: Dict[str, torch.Tensor], cutoff: float, num_rbf: int, device) -> "SchNetWeights":
+    def from_flat(tensors: Dict[str, torch.Tensor], cutoff: float, num_rbf: int, device, rbf_centers=None,
+                  rbf_gamma=None) -> "SchNetWeights":
         nb = len([n for n in tensors if n.endswith(".lin1_w")])
         no = len([n for n in tensors if n.startswith("out") and n.endswith("_w")])
         tt = {n: (torch.as_tensor(v).to(device) if v is not None else None) for n, v in tensors.items()}
-        return SchNetWeights(tt, nb, no, float(cutoff), int(num_rbf))
+        return SchNetWeights(tt, nb, no, float(cutoff), int(num_rbf), rbf_centers=rbf_centers, rbf_gamma=rbf_gamma)
 
 
 @dataclass
@@ -124,9 +132,8 @@ class PriorCSR:
         i32 = torch.int32
         self.n_nodes = n_nodes
         own, rec = [], []
-        ang = [p for p in priors if p.kind == L.PRIOR_ANGLES]
-        dih = [p for p in priors if p.kind == L.PRIOR_DIHEDRALS]
-        assert len(ang) <= 1 and len(dih) <= 1, "condense priors first: at most one angle and one dihedral table"
+        ang = self._merge([p for p in priors if p.kind == L.PRIOR_ANGLES])
+        dih = self._merge([p for p in priors if p.kind == L.PRIOR_DIHEDRALS])
         for p in priors:
             if p.kind not in (L.PRIOR_BONDS, L.PRIOR_REPULSION):
                 continue
@@ -170,6 +177,24 @@ class PriorCSR:
         self.ang = ang[0] if ang else None
         self.dih = dih[0] if dih else None
         self.e_atom = torch.zeros(n_nodes, dtype=torch.float32, device=device)
+
+    @staticmethod
+    def _merge(terms: List[PriorTerm]) -> List[PriorTerm]:
+        """Several tables of one kind (e.g. two angle priors without specialize_priors) -> one concatenated table."""
+        if len(terms) <= 1:
+            return terms
+        if len({t.n_degs for t in terms}) != 1:
+            raise ValueError("dihedral priors with different numbers of Fourier terms cannot share one table")
+
+        def cat(name):
+            vs = [getattr(t, name) for t in terms]
+            if all(v is None for v in vs):
+                return None
+            vs = [v if v is not None else torch.zeros_like(t.p0) for v, t in zip(vs, terms)]
+            return torch.cat(vs, 0).contiguous()
+        return [PriorTerm(terms[0].kind, torch.cat([t.mapping for t in terms], 1).contiguous(),
+                          torch.cat([t.mapping_batch for t in terms], 0).contiguous(), cat("p0"), cat("p1"), cat("p2"),
+                          terms[0].n_degs)]
 
     @staticmethod
     def _ptr(own, n_nodes):
@@ -216,6 +241,11 @@ class ForceField:
         self.mol_ptr = mol_ptr.to(torch.int32).contiguous()
         sizes = (mol_ptr[1:] - mol_ptr[:-1])
         self.max_mol = int(sizes.max().item()) if self.B > 0 else 0
+        if weights is not None and self.max_mol - 1 > self.max_nn:
+            # radius_graph truncates per centre: the list would lose its symmetry (rev = -1 on dropped reverse edges) and
+            # the analytic backward (CFConv over the same list, g_d[e] + g_d[rev e]) would no longer be the gradient
+            raise ValueError(f"a molecule has {self.max_mol} beads but max_num_neighbors = {self.max_nn}: the fused step "
+                             "needs a symmetric neighbour list (max_num_neighbors >= beads per molecule - 1)")
         N, B = self.N, self.B
         f32, i32 = torch.float32, torch.int32
         self.energy = torch.zeros(B, dtype=f32, device=dev)
@@ -557,7 +587,7 @@ class LangevinEngine:
 
     def __init__(self, ff: ForceField, pos: torch.Tensor, vel: torch.Tensor, masses: torch.Tensor,
                  beta: torch.Tensor, dt: float, friction: float, seed: int = 0, use_graph: bool = True,
-                 noise_mode: str = "philox"):
+                 noise_mode: str = "philox", node_offset: int = 0):
         self.ff = ff
         dev = ff.device
         self.pos = pos.detach().to(dev).float().contiguous().clone()
@@ -574,6 +604,9 @@ class LangevinEngine:
         self.vscale = float(np.exp(-dt * friction))                 # langevin.py:76
         self.noisescale = float(np.sqrt(1 - self.vscale * self.vscale))   # langevin.py:77
         self.seed = int(seed) & ((1 << 64) - 1)
+        # global index of this shard's first bead: the Philox counter is (step, node_offset + local bead), so a batch
+        # sharded over several GPUs draws the noise of the unsharded run and no two shards share a stream
+        self.node_offset = int(node_offset)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.ke = torch.zeros(ff.B, dtype=torch.float32, device=dev)
         self.use_graph = use_graph
@@ -591,7 +624,7 @@ class LangevinEngine:
         if noise is None:
             noise = self.noise_buf
         L.call("fmd_baoab_pre", L.ptr(self.pos), L.ptr(self.vel), L.ptr(ff.forces), L.ptr(self.inv_mass),
-               L.ptr(self.noise_std), L.ptr(noise), self.seed, 0, L.ptr(self.step_dev), ff.N, self.dt, self.vscale,
+               L.ptr(self.noise_std), L.ptr(noise), self.seed, 0, L.ptr(self.step_dev), self.node_offset, ff.N, self.dt, self.vscale,
                self.noisescale, st)
         L.call("fmd_increment_u64", L.ptr(self.step_dev), st)
         ff.compute(self.pos)

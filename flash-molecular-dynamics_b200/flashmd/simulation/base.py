@@ -120,7 +120,12 @@ class _Simulation:
         self.exact_cutoff_grad = exact_cutoff_grad
         self.input_option_checks()
         self.random_seed = random_seed
-        self.rng = None if random_seed is None else torch.Generator(device=self.device).manual_seed(random_seed)
+        # replicas sharded over ranks (torchrun) must not share a noise stream: the rank enters the generator seed
+        # (the fused path keys its Philox counters by the global bead index instead, simulation/langevin.py)
+        from .distributed import dist_info
+        _rank, _world = dist_info()
+        _seed = None if random_seed is None else random_seed + (7919 * _rank if _world > 1 else 0)
+        self.rng = None if random_seed is None else torch.Generator(device=self.device).manual_seed(_seed)
         self._simulated = False
         self.checkpointed_data = None
         self.engine = None

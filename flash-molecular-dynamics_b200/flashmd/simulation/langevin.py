@@ -68,13 +68,25 @@ class LangevinSimulation(_Simulation):
         try:
             ff = lower(self.model, data, "w16a16" if self.gptq == "w16a16" else "fp32", self.exact_cutoff_grad)
         except NotLowerable as err:
-            import warnings
-            warnings.warn(f"model is not lowerable to the fused step ({err}); using the module path")
-            return None
+            # no silent second code path: a CUDA fp32 run either uses the fused step or is asked for the module path
+            raise RuntimeError(f"the model cannot be lowered to the fused CUDA step ({err}); set "
+                               "`simulation.force_module_path = True` (CLI: --disable_optim) to run the PyTorch module "
+                               "path on purpose") from err
         seed = self.random_seed if self.random_seed is not None else 0
         return LangevinEngine(ff, data[POSITIONS_KEY], data[VELOCITY_KEY], data[MASS_KEY], self.beta, self.dt,
                               self.friction, seed=seed, use_graph=True,
-                              noise_mode="buffer" if self.noise_source == "torch" else "philox")
+                              noise_mode="buffer" if self.noise_source == "torch" else "philox",
+                              node_offset=self._shard_node_offset())
+
+    def _shard_node_offset(self) -> int:
+        """Global index of this rank's first bead when the replicas are sharded over ranks (equal shards): keys the
+        Philox noise by the GLOBAL bead index, so shards never share a stream and match the unsharded run."""
+        off = getattr(self, "_node_offset", None)
+        if off is not None:
+            return int(off)
+        from .distributed import dist_info
+        rank, world = dist_info()
+        return rank * self.n_sims * self.n_atoms if world > 1 else 0
 
     def _engine_timestep(self, eng):
         if eng.noise_buf is not None:

@@ -13,6 +13,7 @@ from ..models.gradients import GradientsOut, SumOut
 from ..models.mlp import MLP
 from ..models.schnet import SchNet
 from ..models.cutoff import CosineCutoff
+from ..models.radial_basis.gaussian import GaussianBasis
 
 
 class NotLowerable(RuntimeError):
@@ -25,7 +26,8 @@ def _unwrap(m):
 
 def schnet_flat_tensors(net: SchNet) -> Dict[str, torch.Tensor]:
     """nn.Linear-layout ([out, in]) fp32 tensors with the engine's key names."""
-    if not isinstance(net.rbf_layer.cutoff, CosineCutoff) or net.rbf_layer.cutoff.cutoff_lower != 0:
+    if (not isinstance(net.rbf_layer, GaussianBasis) or not isinstance(net.rbf_layer.cutoff, CosineCutoff)
+            or net.rbf_layer.cutoff.cutoff_lower != 0):
         raise NotLowerable("the fused step needs GaussianBasis(CosineCutoff(0, rc))")
     t = {"embedding": net.embedding_layer.weight}
     for l, blk in enumerate(net.interaction_blocks):
@@ -101,8 +103,15 @@ def lower(model: torch.nn.Module, data, precision: str, exact_cutoff_grad: bool 
             if weights is not None:
                 raise NotLowerable("more than one SchNet")
             rc = float(m.rbf_layer.cutoff.cutoff_upper)
-            weights = SchNetWeights.from_flat(schnet_flat_tensors(m), rc, int(m.rbf_layer.num_rbf), dev)
+            # the basis parameters come from the module (a trained GaussianBasis carries its own offset / coeff)
+            weights = SchNetWeights.from_flat(schnet_flat_tensors(m), rc, int(m.rbf_layer.num_rbf), dev,
+                                              rbf_centers=m.rbf_layer.offset.detach(),
+                                              rbf_gamma=float(m.rbf_layer.coeff.detach()))
             max_nn = int(m.max_num_neighbors)
+            sizes = (data.ptr[1:] - data.ptr[:-1])
+            if int(sizes.max()) - 1 > max_nn:
+                raise NotLowerable(f"max_num_neighbors = {max_nn} truncates the neighbour list of a {int(sizes.max())}-bead "
+                                   "molecule: the fused step needs the full symmetric list")
         else:
             priors.append(prior_term(m, data, dev))
     ptr = data.ptr.to(dev)
@@ -116,4 +125,6 @@ def lower(model: torch.nn.Module, data, precision: str, exact_cutoff_grad: bool 
 SchNetWeights.from_module = staticmethod(
     lambda net, device=None: SchNetWeights.from_flat(schnet_flat_tensors(net), float(net.rbf_layer.cutoff.cutoff_upper),
                                                      int(net.rbf_layer.num_rbf),
-                                                     device or net.embedding_layer.weight.device))
+                                                     device or net.embedding_layer.weight.device,
+                                                     rbf_centers=net.rbf_layer.offset.detach(),
+                                                     rbf_gamma=float(net.rbf_layer.coeff.detach())))

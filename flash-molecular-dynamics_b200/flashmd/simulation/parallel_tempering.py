@@ -43,6 +43,7 @@ class PTSimulation(LangevinSimulation):
         self._replica_exchange_attempts = 0
         self._replica_exchange_approved = 0
         self._exchange_index = 0
+        self._pending = []
 
     def attach_model_and_configurations(self, model, configurations, betas: List[float], **kw):
         super().attach_model_and_configurations(model, configurations, betas)
@@ -65,6 +66,7 @@ class PTSimulation(LangevinSimulation):
             lo, hi = shard_range(len(extended), rank, world)
             self._sharded = ShardedExchange(torch.tensor(ext_betas), len(configurations[0].atom_types), rank, world)
             extended, ext_betas = extended[lo:hi], ext_betas[lo:hi]
+            self._node_offset = lo * len(configurations[0].atom_types)     # Philox noise keyed by the global bead index
             if self.filename is not None and not self.filename.endswith(f"_rank{rank}"):
                 self.filename = f"{self.filename}_rank{rank}"
         super()._attach_configurations(extended, ext_betas)
@@ -81,6 +83,18 @@ class PTSimulation(LangevinSimulation):
         return pairs[0], pairs[1]
 
     def _record(self, pair_a, pair_b, approved: torch.Tensor):
+        if approved.is_cuda:
+            # bookkeeping only: resolved at the next save / summary so that an exchange never waits for the GPU
+            self._pending.append((pair_a, pair_b, approved))
+            return
+        self._record_now(pair_a, pair_b, approved)
+
+    def _flush_records(self):
+        for pa, pb, acc in self._pending:
+            self._record_now(pa, pb, acc)
+        self._pending = []
+
+    def _record_now(self, pair_a, pair_b, approved: torch.Tensor):
         approved = approved.cpu().bool()
         self._replica_exchange_approved += int(approved.sum())
         self._replica_exchange_attempts += len(pair_a)
@@ -96,6 +110,19 @@ class PTSimulation(LangevinSimulation):
     # ------------------------------------------------------------------ module path
     def _detect_exchange(self, data) -> Dict:
         pair_a, pair_b = self._get_proposed_pairs()
+        if self._sharded is not None:
+            # sharded module path (CPU / gloo, fp64, ...): pair indices are GLOBAL, the data is local -> the same
+            # all-gather + identical-decision + peer-swap protocol as the fused path
+            from .distributed import exchange_uniforms
+            uni = exchange_uniforms(self.random_seed or 0, self._exchange_index, len(pair_a))
+            x = data[POSITIONS_KEY].detach().clone().contiguous()
+            v = data[VELOCITY_KEY].detach().clone().contiguous()
+            acc = self._sharded.exchange(x, v, data.out[ENERGY_KEY].detach(), pair_a, pair_b, uni,
+                                         self.random_seed or 0, self._exchange_index)
+            self._exchange_index += 1
+            self._record(pair_a, pair_b, acc)
+            data[POSITIONS_KEY], data[VELOCITY_KEY] = x, v
+            return {"a": pair_a[:0], "b": pair_b[:0]}
         u = data.out[ENERGY_KEY]
         beta = self.beta
         p = torch.exp((u[pair_a] - u[pair_b]) * (beta[pair_a] - beta[pair_b])).cpu()
@@ -126,8 +153,9 @@ class PTSimulation(LangevinSimulation):
         pair_a, pair_b = self._get_proposed_pairs()
         if self._sharded is not None:
             from .distributed import exchange_uniforms
-            uni = exchange_uniforms(self.random_seed or 0, self._exchange_index, len(pair_a))
-            acc = self._sharded.exchange(eng.pos, eng.vel, eng.ff.energy, pair_a, pair_b, uni)
+            uni = None if self.exchange_rng == "philox" else exchange_uniforms(self.random_seed or 0, self._exchange_index, len(pair_a))
+            acc = self._sharded.exchange(eng.pos, eng.vel, eng.ff.energy, pair_a, pair_b, uni, self.random_seed or 0,
+                                         self._exchange_index)
             self._exchange_index += 1
             self._record(pair_a, pair_b, acc)
             return
@@ -148,6 +176,7 @@ class PTSimulation(LangevinSimulation):
 
     # ------------------------------------------------------------------ output
     def save_exchanges(self, data, save_step: int) -> None:
+        self._flush_records()
         if self.filename is None:
             return
         np.save(f"{self.filename}_acceptance_{self._get_numpy_count()}.npy", self.acceptance_matrix.cpu().numpy())
@@ -158,6 +187,7 @@ class PTSimulation(LangevinSimulation):
                 "indices_in_the_output": list(range(replica_num * self.n_indep_sims, (replica_num + 1) * self.n_indep_sims))}
 
     def summary(self):
+        self._flush_records()
         att = max(self._replica_exchange_attempts, 1)
         self.exchange_summary = {"attempted": self._replica_exchange_attempts,
                                  "approved": self._replica_exchange_approved,

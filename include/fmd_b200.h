@@ -307,11 +307,13 @@ int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair_ptr, const
 
 /* replaces: LangevinSimulation.timestep B-A-O-A (simulation/langevin.py:137-157).
  * In place on pos/vel [n_nodes,3]. noise: external N(0,1) [n_nodes,3] or NULL -> counter-based
- * Philox4x32-10 keyed by (seed), counter (step [+ *step_dev when non-NULL], node) + Box-Muller.
+ * Philox4x32-10 keyed by (seed), counter (step [+ *step_dev when non-NULL], node_offset + node) + Box-Muller:
+ * node_offset = global index of this shard's first bead, so that a replica batch sharded over several GPUs draws
+ * exactly the noise of the unsharded run (and no two shards share a stream).
  * inv_mass = 1/m [n_nodes]; noise_std = sqrt(1/(beta m)) [n_nodes] (beta_mass_ratio, :211-215). */
 int fmd_baoab_pre(float* pos, float* vel, const float* forces, const float* inv_mass, const float* noise_std,
-                  const float* noise, uint64_t seed, uint64_t step, const uint64_t* step_dev, int n_nodes,
-                  float dt, float vscale, float noisescale, void* stream);
+                  const float* noise, uint64_t seed, uint64_t step, const uint64_t* step_dev, uint64_t node_offset,
+                  int n_nodes, float dt, float vscale, float noisescale, void* stream);
 
 /* *counter += 1 on the stream (keeps the Philox step counter on the device so a captured CUDA
  * graph of the whole step can be replayed; fmd_baoab_pre adds *step_dev to `step`). */

@@ -39,12 +39,17 @@ def main():
         u = exchange_uniforms(11, k, len(pa))
         acc = ex.exchange(x, v, e_all[lo:hi].to(dev), pa, pb, u)
         acc_ref = u < torch.exp((e_all[pa] - e_all[pb]) * (beta_all[pa] - beta_all[pb]))
-        assert torch.equal(acc, acc_ref)
+        assert torch.equal(acc.cpu().bool(), acc_ref)
         x_ref, v_ref = _reference_exchange(x_ref, v_ref, beta_all, pa, pb, acc_ref, n_atoms)
         assert torch.equal(x.cpu(), x_ref[lo * n_atoms:hi * n_atoms]), (rank, k)
         assert torch.allclose(v.cpu(), v_ref[lo * n_atoms:hi * n_atoms], rtol=1e-6, atol=0), (rank, k)
+    # counter-based decisions (no uniforms at all): identical on every rank without communication
+    acc = ex.exchange(x, v, e_all[lo:hi].to(dev), even[0], even[1], None, seed=5, exchange_index=3)
+    allacc = [torch.empty_like(acc) for _ in range(world)]
+    dist.all_gather(allacc, acc)
+    assert all(torch.equal(a, allacc[0]) for a in allacc)
     if rank == 0:
-        print(f"[dist_check] NCCL sharded exchange == reference on {world} GPUs")
+        print(f"[dist_check] NCCL sharded exchange == reference on {world} GPUs (device-side decide / select, no host read)")
     # ---- PT simulation sharded over the ranks
     from helpers import dropin_model_from_golden, load_golden
     from flashmd.simulation import PTSimulation
@@ -58,7 +63,14 @@ def main():
     sim.attach_model_and_configurations(model, [configs[i % len(configs)] for i in range(world)],
                                         betas=[1.67, 1.42, 1.16, 1.0])
     assert sim.n_sims == 4 * world // world
+    assert sim._node_offset == rank * sim.n_sims * sim.n_atoms      # Philox noise keyed by the global bead index
     sim.simulate()
+    # shards must not share a noise stream: the velocities of local replica 0 differ between ranks
+    v0 = sim.engine.vel[: sim.n_atoms].clone()
+    vs = [torch.empty_like(v0) for _ in range(world)]
+    dist.all_gather(vs, v0)
+    if world > 1:
+        assert not torch.allclose(vs[0], vs[1])
     m = sim.get_throughput_metrics()
     ok = np.isfinite(sim.simulated_coords).all() and m["path"] == "fused-engine"
     t = torch.tensor([int(ok), sim.exchange_summary["approved"]], device=dev)
