@@ -280,7 +280,7 @@ def main():
     if world > 1:
         # NCCL's own log (communicator size, NVLS / ring choice) is kept, but away from stdout (one JSON line there)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fmd_nccl_%h_%p.log")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -405,7 +405,8 @@ def main():
         }
         if dist is not None:
             line["nccl"] = {"nranks": world, "version": ".".join(str(v) for v in torch.cuda.nccl.version()),
-                            "data_path_collectives_per_step": 0, "log": os.environ.get("NCCL_DEBUG_FILE")}
+                            "data_path_collectives_per_step": 0, "log": os.environ.get("NCCL_DEBUG_FILE"),
+                            "log_excerpt": nccl_log_excerpt()}
         if world == 1 and not args.no_triton_baseline and args.precision == "w16a16" and args.blocks == 3:
             line["triton_baseline"] = triton_baseline_entry(args, value)
         if world == 1 and not args.no_cpu_baseline:
@@ -413,6 +414,26 @@ def main():
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def nccl_log_excerpt():
+    """Communicator lines of this process's NCCL log (NCCL_DEBUG_FILE), so that the bench line itself shows the ranks."""
+    import glob
+    import socket
+    pat = os.environ.get("NCCL_DEBUG_FILE", "")
+    if not pat or pat.startswith("/dev/"):
+        return None
+    path = pat.replace("%h", socket.gethostname()).replace("%p", str(os.getpid()))
+    files = [path] if os.path.exists(path) else sorted(glob.glob(pat.replace("%h", "*").replace("%p", "*")))[-1:]
+    out = []
+    for f in files:
+        try:
+            for ln in open(f, errors="replace"):
+                if "nranks" in ln or "Init COMPLETE" in ln or "NVLS" in ln:
+                    out.append(ln.strip()[-220:])
+        except OSError:
+            pass
+    return out[:6] or None
 
 
 def triton_baseline_entry(args, our_value):
@@ -549,7 +570,8 @@ def run_pt(args, rank, world, local, dev, dist):
             "edges": edges_now, "edges_start": edges_start, "nodes": B * n, "per_rank": per_rank,
             "exchanges": {"n": n_blocks, "pairs_proposed": int(sum(a.numel() for a in accs[2:])), "pairs_accepted": n_acc,
                           "rng": "Philox keyed by (seed, exchange index, pair), identical on every rank"},
-            "nccl": None if dist is None else {"nranks": world, "version": ".".join(str(v) for v in torch.cuda.nccl.version())}}))
+            "nccl": None if dist is None else {"nranks": world, "version": ".".join(str(v) for v in torch.cuda.nccl.version()),
+                                               "log_excerpt": nccl_log_excerpt()}}))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -188,6 +188,25 @@ baoab_pre_kernel(float* __restrict__ pos, float* __restrict__ vel, const float* 
   }
 }
 
+// Overdamped Langevin (Brownian) step: x += F D dt + sqrt(2 D dt) xi, dtau = D dt per bead
+__global__ void __launch_bounds__(256)
+overdamped_kernel(float* __restrict__ pos, const float* __restrict__ forces, const float* __restrict__ dtau,
+                  const float* __restrict__ noise, uint64_t seed, uint64_t step, const uint64_t* __restrict__ step_dev,
+                  uint64_t node_offset, int n_nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  if (step_dev) step += *step_dev;
+  float z[3];
+  if (noise) {
+    z[0] = noise[3 * i]; z[1] = noise[3 * i + 1]; z[2] = noise[3 * i + 2];
+  } else {
+    normal3(seed, step, node_offset + (uint64_t)i, z[0], z[1], z[2]);
+  }
+  const float dt_ = dtau[i], amp = sqrtf(2.0f * dt_);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) pos[3 * i + d] = pos[3 * i + d] + forces[3 * i + d] * dt_ + amp * z[d];
+}
+
 __global__ void __launch_bounds__(256)
 baoab_post_kernel(float* __restrict__ vel, const float* __restrict__ forces, const float* __restrict__ inv_mass,
                   int n_nodes, float dt) {
@@ -364,6 +383,17 @@ extern "C" int fmd_baoab_pre(float* pos, float* vel, const float* forces, const 
   baoab_pre_kernel<<<fmd_div_up(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(pos, vel, forces, inv_mass, noise_std,
                                                                                 noise, seed, step, step_dev, node_offset, n_nodes, dt,
                                                                                 vscale, noisescale);
+  FMD_CHECK_LAUNCH();
+  return FMD_OK;
+}
+
+extern "C" int fmd_overdamped_step(float* pos, const float* forces, const float* dtau, const float* noise, uint64_t seed,
+                                   uint64_t step, const uint64_t* step_dev, uint64_t node_offset, int n_nodes,
+                                   void* stream) {
+  FMD_REQUIRE(pos && forces && dtau, "fmd_overdamped_step: bad arguments");
+  if (n_nodes == 0) return FMD_OK;
+  overdamped_kernel<<<fmd_div_up(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(pos, forces, dtau, noise, seed, step,
+                                                                                 step_dev, node_offset, n_nodes);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

@@ -8,6 +8,13 @@
 //   repulsion  (sigma / d)^6              prior/repulsion.py:119-122
 //   angles     k (cos(theta) - x0)^2 + V0 prior/harmonic.py:122-123, internal_coordinates.py:140-170
 //   dihedrals  v0 + sum_n k1_n sin(n phi) + k2_n cos(n phi)   prior/fourier_series.py:154-192, :174-223
+// and the remaining prior classes of the reference (a model that contains one stays on the fused step):
+//   polynomial bonds      V0 + sum_{n=1..4} k_n d^n                  prior/polynomial.py:13-186
+//   polynomial angles     V0 + sum_{n=1..6} k_n cos^n                (QuarticAngles)
+//   restricted bending    a c^4 + b c^3 + c c^2 + d c + k / sin^2 + V0   prior/restricted_bending.py:13-238
+//   raw-angle harmonic    k (theta - x0)^2                            prior/harmonic.py:267-300
+//   (shifted) harmonic impropers  k (x - x0)^2, x = phi or (phi < 0 ? phi + 2 pi : phi) - pi   prior/harmonic.py:230-265, 327-405
+// Angle-like terms share ONE table with a per-term form code, improper-like terms a second one.
 // A term's energy is split evenly between its beads (1/2, 1/3, 1/4) so that the per-molecule sum
 // (fmd_segment_sum) reproduces scatter(y, mapping_batch) of the reference.
 #include "fmd_common.cuh"
@@ -41,9 +48,10 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
                  const void* __restrict__ pair_ent_v, const float4* __restrict__ pair_tab,
                  const int32_t* __restrict__ mb_ptr,
                  const int32_t* __restrict__ mb_ent, const int32_t* __restrict__ ang_map, int n_ang,
-                 const float* __restrict__ ang_k, const float* __restrict__ ang_x0, const float* __restrict__ ang_v0,
+                 const float4* __restrict__ ang_par,
                  const int32_t* __restrict__ dih_map, int n_dih, const float* __restrict__ dih_k1,
                  const float* __restrict__ dih_k2, const float* __restrict__ dih_v0, int n_degs,
+                 const int32_t* __restrict__ imp_map, int n_imp, const float4* __restrict__ imp_par,
                  float* __restrict__ e_atom, float* __restrict__ forces, int accumulate_forces) {
   const int lane = threadIdx.x & 31;
   const int a = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -56,23 +64,28 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
     const int p1 = __ldg(&pair_ptr[a + 1]);
 #pragma unroll 8   // independent record -> position load chains in flight (the loop is latency-bound on the record stream)
     for (int p = __ldg(&pair_ptr[a]) + lane; p < p1; p += 32) {
-      int head;
-      float q0, q1, q2;
+      int head, tab_id = 0;
+      float q0, q1, q2, q3 = 0.f;
       if (PACKED) {
         const int2 ent = __ldg(reinterpret_cast<const int2*>(pair_ent_v) + p);
-        const float4 q = __ldg(&pair_tab[ent.y]);
-        head = ent.x; q0 = q.x; q1 = q.y; q2 = q.z;
+        const float4 q = __ldg(&pair_tab[2 * ent.y]);      // two float4 per parameter id (the second: polynomial terms only)
+        head = ent.x; tab_id = ent.y; q0 = q.x; q1 = q.y; q2 = q.z; q3 = q.w;
       } else {
         const int4 ent = __ldg(reinterpret_cast<const int4*>(pair_ent_v) + p);
         head = ent.x; q0 = __int_as_float(ent.y); q1 = __int_as_float(ent.z); q2 = __int_as_float(ent.w);
       }
-      const int other = head & 0x0FFFFFFF, kind = head >> 28;
+      const int other = head & 0x0FFFFFFF, kind = (int)((unsigned)head >> 28);
       const V3 dr = sub(ld3(pos, other), pa);
       const float d = sqrtf(dot(dr, dr));
       float et, dEdd;
       if (kind == FMD_PRIOR_BONDS) {
         et = q0 * (d - q1) * (d - q1) + q2;
         dEdd = 2.0f * q0 * (d - q1);
+      } else if (kind == FMD_PRIOR_POLY_BONDS) {
+        // V0 + k1 d + k2 d^2 + k3 d^3 + k4 d^4 (PACKED only: V0 sits in the second float4 of the table row)
+        const float v0 = PACKED ? __ldg(&pair_tab[2 * tab_id + 1]).x : 0.f;
+        et = v0 + d * (q0 + d * (q1 + d * (q2 + d * q3)));
+        dEdd = q0 + d * (2.0f * q1 + d * (3.0f * q2 + d * 4.0f * q3));
       } else {
         const float sg = q0 / d, rr = sg * sg;
         et = rr * rr * rr;
@@ -88,37 +101,64 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
     const int q1 = __ldg(&mb_ptr[a + 1]);
     for (int q = __ldg(&mb_ptr[a]) + lane; q < q1; q += 32) {
       const int ent = __ldg(&mb_ent[q]);
-      const int t = ent & 0x0FFFFFFF, role = (ent >> 28) & 3;
-      if (!((ent >> 30) & 1)) {
+      const int t = ent & 0x0FFFFFFF, role = (ent >> 28) & 3, table = (int)((unsigned)ent >> 30);
+      if (table == 0) {
         const int i = __ldg(&ang_map[t]), j = __ldg(&ang_map[n_ang + t]), k_ = __ldg(&ang_map[2 * n_ang + t]);
         const V3 d1 = sub(ld3(pos, i), ld3(pos, j)), d2 = sub(ld3(pos, k_), ld3(pos, j));
         const float n1 = sqrtf(dot(d1, d1)), n2 = sqrtf(dot(d2, d2));
         const float inv = 1.0f / (n1 * n2);
         const float c = dot(d1, d2) * inv;
-        const float k = __ldg(&ang_k[t]), x0 = __ldg(&ang_x0[t]);
-        const float et = k * (c - x0) * (c - x0) + (ang_v0 ? __ldg(&ang_v0[t]) : 0.f);
-        const float dEdc = 2.0f * k * (c - x0);
+        // per-term record: {p0..p3}, {p4, p5, V0, form}
+        const float4 pa4 = __ldg(&ang_par[2 * t]), pb4 = __ldg(&ang_par[2 * t + 1]);
+        const int form = __float_as_int(pb4.w);
+        float et, dEdc;
+        if (form == FMD_ANGLE_HARMONIC_COS) {
+          et = pa4.x * (c - pa4.y) * (c - pa4.y);
+          dEdc = 2.0f * pa4.x * (c - pa4.y);
+        } else if (form == FMD_ANGLE_POLY_COS) {
+          et = c * (pa4.x + c * (pa4.y + c * (pa4.z + c * (pa4.w + c * (pb4.x + c * pb4.y)))));
+          dEdc = pa4.x + c * (2.0f * pa4.y + c * (3.0f * pa4.z + c * (4.0f * pa4.w + c * (5.0f * pb4.x + c * 6.0f * pb4.y))));
+        } else if (form == FMD_ANGLE_RESTRICTED) {
+          const float s2 = fmaxf(1.0f - c * c, 1e-12f);
+          et = c * (pa4.w + c * (pa4.z + c * (pa4.y + c * pa4.x))) + pb4.x / s2;
+          dEdc = pa4.w + c * (2.0f * pa4.z + c * (3.0f * pa4.y + c * 4.0f * pa4.x)) + 2.0f * pb4.x * c / (s2 * s2);
+        } else {   // FMD_ANGLE_HARMONIC_RAW: k (theta - x0)^2, d theta / d cos = -1 / sin
+          const float cc = fminf(fmaxf(c, -1.0f), 1.0f);
+          const float th = acosf(cc), sn = sqrtf(fmaxf(1.0f - cc * cc, 1e-12f));
+          et = pa4.x * (th - pa4.y) * (th - pa4.y);
+          dEdc = -2.0f * pa4.x * (th - pa4.y) / sn;
+        }
+        et += pb4.z;
         const V3 gi = mul(sub(mul(d2, inv), mul(d1, c / (n1 * n1))), dEdc);
         const V3 gk = mul(sub(mul(d1, inv), mul(d2, c / (n2 * n2))), dEdc);
         const V3 g = role == 0 ? gi : (role == 2 ? gk : mul(add(gi, gk), -1.f));
         f = sub(f, g);
         e += et * (1.0f / 3.0f);
       } else {
-        const int i = __ldg(&dih_map[t]), j = __ldg(&dih_map[n_dih + t]), k_ = __ldg(&dih_map[2 * n_dih + t]),
-                  l = __ldg(&dih_map[3 * n_dih + t]);
+        const int32_t* __restrict__ map = table == 1 ? dih_map : imp_map;
+        const int nt = table == 1 ? n_dih : n_imp;
+        const int i = __ldg(&map[t]), j = __ldg(&map[nt + t]), k_ = __ldg(&map[2 * nt + t]), l = __ldg(&map[3 * nt + t]);
         const V3 b1 = sub(ld3(pos, j), ld3(pos, i)), b2 = sub(ld3(pos, k_), ld3(pos, j)),
                  b3 = sub(ld3(pos, l), ld3(pos, k_));
         const V3 m = cross(b1, b2), n = cross(b2, b3);
         const float b2sq = dot(b2, b2), nb2 = sqrtf(b2sq);
         const float phi = atan2f(nb2 * dot(b1, n), dot(m, n));
-        float dEdphi = 0.f;
-        float et = dih_v0 ? __ldg(&dih_v0[t]) : 0.f;
-        for (int d = 0; d < n_degs; ++d) {
-          float s, c;
-          sincosf((float)(d + 1) * phi, &s, &c);
-          const float k1 = __ldg(&dih_k1[(size_t)t * n_degs + d]), k2 = __ldg(&dih_k2[(size_t)t * n_degs + d]);
-          et += k1 * s + k2 * c;
-          dEdphi += (float)(d + 1) * (k1 * c - k2 * s);
+        float dEdphi = 0.f, et;
+        if (table == 1) {
+          et = dih_v0 ? __ldg(&dih_v0[t]) : 0.f;
+          for (int d = 0; d < n_degs; ++d) {
+            float s, c;
+            sincosf((float)(d + 1) * phi, &s, &c);
+            const float k1 = __ldg(&dih_k1[(size_t)t * n_degs + d]), k2 = __ldg(&dih_k2[(size_t)t * n_degs + d]);
+            et += k1 * s + k2 * c;
+            dEdphi += (float)(d + 1) * (k1 * c - k2 * s);
+          }
+        } else {
+          const float4 pp = __ldg(&imp_par[t]);     // {k, x0, V0, form}
+          float x = phi;
+          if (__float_as_int(pp.w) == FMD_IMPROPER_SHIFTED) x = (phi < 0.f ? phi + 2.0f * FMD_PI_F : phi) - FMD_PI_F;
+          et = pp.x * (x - pp.y) * (x - pp.y) + pp.z;
+          dEdphi = 2.0f * pp.x * (x - pp.y);
         }
         const V3 gi = mul(m, -nb2 / dot(m, m));
         const V3 gl = mul(n, nb2 / dot(n, n));
@@ -155,24 +195,27 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
 
 extern "C" int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair_ptr, const void* pair_ent,
                               const float* pair_tab, const int32_t* mb_ptr, const int32_t* mb_ent, const int32_t* ang_map, int n_ang,
-                              const float* ang_k, const float* ang_x0, const float* ang_v0, const int32_t* dih_map,
-                              int n_dih, const float* dih_k1, const float* dih_k2, const float* dih_v0, int n_degs,
-                              float* e_atom, float* forces, int accumulate_forces, void* stream) {
+                              const float* ang_par, const int32_t* dih_map, int n_dih, const float* dih_k1,
+                              const float* dih_k2, const float* dih_v0, int n_degs, const int32_t* imp_map, int n_imp,
+                              const float* imp_par, float* e_atom, float* forces, int accumulate_forces, void* stream) {
   FMD_REQUIRE(pos && e_atom && forces, "fmd_priors_csr: bad arguments");
   FMD_REQUIRE(!pair_ptr || pair_ent, "fmd_priors_csr: pair_ptr without pair entries");
   FMD_REQUIRE(!mb_ptr || mb_ent, "fmd_priors_csr: mb_ptr without entries");
-  FMD_REQUIRE(n_ang == 0 || (ang_map && ang_k && ang_x0), "fmd_priors_csr: missing angle tables");
+  FMD_REQUIRE(n_ang == 0 || (ang_map && ang_par), "fmd_priors_csr: missing angle tables");
   FMD_REQUIRE(n_dih == 0 || (dih_map && dih_k1 && dih_k2), "fmd_priors_csr: missing dihedral tables");
+  FMD_REQUIRE(n_imp == 0 || (imp_map && imp_par), "fmd_priors_csr: missing improper tables");
   if (n_nodes <= 0) return FMD_OK;
   const int grid = fmd_div_up(n_nodes, WARPS);
   if (pair_tab)
     prior_csr_kernel<true><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
-        pos, n_nodes, pair_ptr, pair_ent, (const float4*)pair_tab, mb_ptr, mb_ent, ang_map, n_ang, ang_k, ang_x0, ang_v0,
-        dih_map, n_dih, dih_k1, dih_k2, dih_v0, n_degs, e_atom, forces, accumulate_forces);
+        pos, n_nodes, pair_ptr, pair_ent, (const float4*)pair_tab, mb_ptr, mb_ent, ang_map, n_ang, (const float4*)ang_par,
+        dih_map, n_dih, dih_k1, dih_k2, dih_v0, n_degs, imp_map, n_imp, (const float4*)imp_par, e_atom, forces,
+        accumulate_forces);
   else
     prior_csr_kernel<false><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
-        pos, n_nodes, pair_ptr, pair_ent, nullptr, mb_ptr, mb_ent, ang_map, n_ang, ang_k, ang_x0, ang_v0,
-        dih_map, n_dih, dih_k1, dih_k2, dih_v0, n_degs, e_atom, forces, accumulate_forces);
+        pos, n_nodes, pair_ptr, pair_ent, nullptr, mb_ptr, mb_ent, ang_map, n_ang, (const float4*)ang_par,
+        dih_map, n_dih, dih_k1, dih_k2, dih_v0, n_degs, imp_map, n_imp, (const float4*)imp_par, e_atom, forces,
+        accumulate_forces);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

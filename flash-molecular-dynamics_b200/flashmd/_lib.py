@@ -18,6 +18,10 @@ LIB_PATH = os.path.join(_CSRC, "libfmd_b200.so")
 F32, F16 = 0, 1
 ACT_NONE, ACT_TANH, ACT_TANH_CLAMPED = 0, 1, 2
 PRIOR_BONDS, PRIOR_ANGLES, PRIOR_DIHEDRALS, PRIOR_REPULSION = 0, 1, 2, 3
+# kinds evaluated by fmd_priors_csr only (the fused step): polynomial bonds, the other angle forms, impropers
+PRIOR_POLY_BONDS, PRIOR_POLY_ANGLES, PRIOR_RESTRICTED_ANGLES, PRIOR_RAW_ANGLES, PRIOR_IMPROPERS, PRIOR_SHIFTED_IMPROPERS = 4, 5, 6, 7, 8, 9
+ANGLE_FORM = {1: 0, 5: 1, 6: 2, 7: 3}      # PRIOR_* kind -> FMD_ANGLE_* form code
+IMPROPER_FORM = {8: 0, 9: 1}
 
 _lib = None
 
@@ -75,11 +79,13 @@ _SIGS = {
     "fmd_segment_sum": ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
     "fmd_prior_energy_forces": ([c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p], c_int),
-    "fmd_priors_csr": ([c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                        c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
-                        c_void_p], c_int),
+    "fmd_priors_csr": ([c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                        c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                        c_int, c_void_p], c_int),
     "fmd_baoab_pre": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p,
                        c_uint64, c_int, c_float, c_float, c_float, c_void_p], c_int),
+    "fmd_overdamped_step": ([c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_uint64, c_int,
+                             c_void_p], c_int),
     "fmd_increment_u64": ([c_void_p, c_void_p], c_int),
     "fmd_baoab_post": ([c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p], c_int),
     "fmd_philox_normal": ([c_uint64, c_uint64, c_int, c_void_p, c_void_p], c_int),

@@ -126,61 +126,119 @@ class PriorTerm:
 
 
 class PriorCSR:
-    """Static incidence CSR of all prior terms (built once): what fmd_priors_csr consumes."""
+    """Static incidence CSR of all prior terms (built once): what fmd_priors_csr consumes.
+
+    Two-body kinds (bonds, polynomial bonds, repulsion) become 8-byte incidence records + a deduplicated parameter
+    table; all angle-like kinds share one [n,8] table with a per-term form code, improper-like kinds another, the
+    Fourier dihedrals keep their k1 / k2 arrays."""
+
+    PAIR_KINDS = (L.PRIOR_BONDS, L.PRIOR_REPULSION, L.PRIOR_POLY_BONDS)
 
     def __init__(self, priors: List[PriorTerm], n_nodes: int, device):
         i32 = torch.int32
         self.n_nodes = n_nodes
-        own, rec = [], []
-        ang = self._merge([p for p in priors if p.kind == L.PRIOR_ANGLES])
+        own, others, rec = [], [], []
+        ang = [p for p in priors if p.kind in L.ANGLE_FORM]
+        imp = [p for p in priors if p.kind in L.IMPROPER_FORM]
         dih = self._merge([p for p in priors if p.kind == L.PRIOR_DIHEDRALS])
+        known = set(self.PAIR_KINDS) | set(L.ANGLE_FORM) | set(L.IMPROPER_FORM) | {L.PRIOR_DIHEDRALS}
         for p in priors:
-            if p.kind not in (L.PRIOR_BONDS, L.PRIOR_REPULSION):
+            if p.kind not in known:
+                raise ValueError(f"unknown prior kind {p.kind}")
+        for p in priors:
+            if p.kind not in self.PAIR_KINDS:
                 continue
             i, j = p.mapping[0].long(), p.mapping[1].long()
             assert int(p.mapping.max()) < (1 << 28)
-            z = torch.zeros_like(p.p0)
-            q1 = p.p1 if (p.kind == L.PRIOR_BONDS and p.p1 is not None) else z
-            q2 = p.p2 if (p.kind == L.PRIOR_BONDS and p.p2 is not None) else z
+            nt = p.n_terms
+            par = torch.zeros((nt, 5), dtype=torch.float32, device=device)
+            if p.kind == L.PRIOR_POLY_BONDS:       # p0 = ks [n_terms, n_degs <= 4], p2 = V0
+                ks = p.p0.float().reshape(nt, -1)
+                if ks.shape[1] > 4:
+                    raise ValueError("polynomial bond priors up to degree 4 are supported by the fused step")
+                par[:, :ks.shape[1]] = ks
+                if p.p2 is not None:
+                    par[:, 4] = p.p2.float().flatten()
+            else:
+                par[:, 0] = p.p0.float().flatten()
+                if p.kind == L.PRIOR_BONDS:
+                    if p.p1 is not None:
+                        par[:, 1] = p.p1.float().flatten()
+                    if p.p2 is not None:
+                        par[:, 2] = p.p2.float().flatten()
+            kcol = torch.full((nt, 1), float(p.kind), device=device)
             for a, b in ((i, j), (j, i)):
                 own.append(a)
-                rec.append(torch.stack([(b | (p.kind << 28)).to(i32), p.p0.float().view(i32), q1.float().view(i32),
-                                        q2.float().view(i32)], 1))
+                others.append(b)
+                rec.append(torch.cat([kcol, par], 1))                          # [kind, p0..p4]
         self.pair_ptr = self.pair_ent = self.pair_tab = None
         if own:
-            own, rec = torch.cat(own), torch.cat(rec)
+            own, others, rec = torch.cat(own), torch.cat(others), torch.cat(rec)
             order = torch.argsort(own, stable=True)
-            rec = rec[order].contiguous()
-            # 8-byte records + deduplicated parameter table (a few hundred distinct (kind, k, x0, V0 | sigma) tuples)
-            key = torch.cat([(rec[:, :1] >> 28), rec[:, 1:]], 1)
+            rec, others = rec[order], others[order]
+            key = rec.contiguous().view(torch.int32)                         # (kind, p0..p4) bit patterns
             uniq, inv = torch.unique(key, dim=0, return_inverse=True)
-            if uniq.shape[0] <= 65536:
-                self.pair_tab = torch.cat([uniq[:, 1:], torch.zeros_like(uniq[:, :1])], 1).contiguous().view(torch.float32)
-                self.pair_ent = torch.stack([rec[:, 0], inv.to(i32)], 1).contiguous()
-            else:
-                self.pair_ent = rec
+            tab = torch.zeros((uniq.shape[0], 8), dtype=torch.float32, device=device)
+            tab[:, :5] = uniq[:, 1:].contiguous().view(torch.float32)
+            self.pair_tab = tab.contiguous()
+            kind = rec[:, 0].long()
+            self.pair_ent = torch.stack([(others | (kind << 28)).to(i32), inv.to(i32)], 1).contiguous()
             self.pair_ptr = self._ptr(own, n_nodes)
+        # ---- angle-like terms: one table {p0..p5, V0, form}
+        self.ang_map = self.ang_par = None
+        if ang:
+            maps, pars = [], []
+            for p in ang:
+                nt = p.n_terms
+                row = torch.zeros((nt, 8), dtype=torch.float32, device=device)
+                if p.kind in (L.PRIOR_ANGLES, L.PRIOR_RAW_ANGLES):
+                    row[:, 0], row[:, 1] = p.p0.float().flatten(), p.p1.float().flatten()
+                else:                                   # polynomial (k1..k6) / restricted (a, b, c, d, k): p0 = [n_terms, m]
+                    ks = p.p0.float().reshape(nt, -1)
+                    if ks.shape[1] > 6:
+                        raise ValueError("polynomial angle priors up to degree 6 are supported by the fused step")
+                    row[:, :ks.shape[1]] = ks
+                if p.p2 is not None:
+                    row[:, 6] = p.p2.float().flatten()
+                row[:, 7] = torch.full((nt,), L.ANGLE_FORM[p.kind], dtype=i32, device=device).view(torch.float32)
+                maps.append(p.mapping)
+                pars.append(row)
+            self.ang_map, self.ang_par = torch.cat(maps, 1).to(i32).contiguous(), torch.cat(pars, 0).contiguous()
+        self.imp_map = self.imp_par = None
+        if imp:
+            maps, pars = [], []
+            for p in imp:
+                nt = p.n_terms
+                row = torch.zeros((nt, 4), dtype=torch.float32, device=device)
+                row[:, 0], row[:, 1] = p.p0.float().flatten(), p.p1.float().flatten()
+                if p.p2 is not None:
+                    row[:, 2] = p.p2.float().flatten()
+                row[:, 3] = torch.full((nt,), L.IMPROPER_FORM[p.kind], dtype=i32, device=device).view(torch.float32)
+                maps.append(p.mapping)
+                pars.append(row)
+            self.imp_map, self.imp_par = torch.cat(maps, 1).to(i32).contiguous(), torch.cat(pars, 0).contiguous()
         own, ent = [], []
-        for isd, group in ((0, ang), (1, dih)):
-            for p in group:
-                t = torch.arange(p.n_terms, device=device, dtype=torch.int64)
-                assert p.n_terms < (1 << 28)
-                for r in range(p.mapping.shape[0]):
-                    own.append(p.mapping[r].long())
-                    ent.append((t | (r << 28) | (isd << 30)).to(i32))
+        for table, mapping in ((0, self.ang_map), (1, dih[0].mapping if dih else None), (2, self.imp_map)):
+            if mapping is None:
+                continue
+            nt = mapping.shape[1]
+            assert nt < (1 << 28)
+            t = torch.arange(nt, device=device, dtype=torch.int64)
+            for r in range(mapping.shape[0]):
+                own.append(mapping[r].long())
+                ent.append((t | (r << 28) | (table << 30)).to(i32))
         self.mb_ptr = self.mb_ent = None
         if own:
             own, ent = torch.cat(own), torch.cat(ent)
             order = torch.argsort(own, stable=True)
             self.mb_ent = ent[order].contiguous()
             self.mb_ptr = self._ptr(own, n_nodes)
-        self.ang = ang[0] if ang else None
         self.dih = dih[0] if dih else None
         self.e_atom = torch.zeros(n_nodes, dtype=torch.float32, device=device)
 
     @staticmethod
     def _merge(terms: List[PriorTerm]) -> List[PriorTerm]:
-        """Several tables of one kind (e.g. two angle priors without specialize_priors) -> one concatenated table."""
+        """Several Fourier-dihedral tables (no specialize_priors) -> one concatenated table."""
         if len(terms) <= 1:
             return terms
         if len({t.n_degs for t in terms}) != 1:
@@ -190,7 +248,8 @@ class PriorCSR:
             vs = [getattr(t, name) for t in terms]
             if all(v is None for v in vs):
                 return None
-            vs = [v if v is not None else torch.zeros_like(t.p0) for v, t in zip(vs, terms)]
+            vs = [v if v is not None else torch.zeros_like(t.p0[:, 0] if name == "p2" and t.p0.dim() > 1 else t.p0)
+                  for v, t in zip(vs, terms)]
             return torch.cat(vs, 0).contiguous()
         return [PriorTerm(terms[0].kind, torch.cat([t.mapping for t in terms], 1).contiguous(),
                           torch.cat([t.mapping_batch for t in terms], 0).contiguous(), cat("p0"), cat("p1"), cat("p2"),
@@ -204,13 +263,14 @@ class PriorCSR:
         return ptr.to(torch.int32).contiguous()
 
     def launch(self, pos, forces, accumulate, st):
-        a, d = self.ang, self.dih
+        d = self.dih
         L.call("fmd_priors_csr", L.ptr(pos), self.n_nodes, L.ptr(self.pair_ptr), L.ptr(self.pair_ent), L.ptr(self.pair_tab),
-               L.ptr(self.mb_ptr),
-               L.ptr(self.mb_ent), L.ptr(a.mapping) if a else None, a.n_terms if a else 0, L.ptr(a.p0) if a else None,
-               L.ptr(a.p1) if a else None, L.ptr(a.p2) if a else None, L.ptr(d.mapping) if d else None,
-               d.n_terms if d else 0, L.ptr(d.p0) if d else None, L.ptr(d.p1) if d else None,
-               L.ptr(d.p2) if d else None, d.n_degs if d else 1, L.ptr(self.e_atom), L.ptr(forces), int(accumulate), st)
+               L.ptr(self.mb_ptr), L.ptr(self.mb_ent),
+               L.ptr(self.ang_map), self.ang_map.shape[1] if self.ang_map is not None else 0, L.ptr(self.ang_par),
+               L.ptr(d.mapping) if d else None, d.n_terms if d else 0, L.ptr(d.p0) if d else None, L.ptr(d.p1) if d else None,
+               L.ptr(d.p2) if d else None, d.n_degs if d else 1,
+               L.ptr(self.imp_map), self.imp_map.shape[1] if self.imp_map is not None else 0, L.ptr(self.imp_par),
+               L.ptr(self.e_atom), L.ptr(forces), int(accumulate), st)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -672,6 +732,30 @@ class LangevinEngine:
         """<2 KE / (3 n)> per molecule in energy units (equipartition: kT = 2 KE / dof)."""
         sizes = (self.ff.mol_ptr[1:] - self.ff.mol_ptr[:-1]).float()
         return 2.0 * self.ke / (3.0 * sizes)
+
+
+class OverdampedEngine(LangevinEngine):
+    """Overdamped Langevin steps (reference simulation/langevin.py:315-420) over a ForceField on the same fixed buffers /
+    CUDA graph as LangevinEngine:  x += F D dt + sqrt(2 D dt) xi,  D = 1 / (beta friction) per bead.  No velocities."""
+
+    def __init__(self, ff: ForceField, pos: torch.Tensor, beta: torch.Tensor, dt: float, friction: float, seed: int = 0,
+                 use_graph: bool = True, noise_mode: str = "philox", node_offset: int = 0):
+        n = ff.N
+        super().__init__(ff, pos, torch.zeros((n, 3)), torch.ones(n), beta, dt, friction, seed=seed, use_graph=use_graph,
+                         noise_mode=noise_mode, node_offset=node_offset)
+        sizes = (ff.mol_ptr[1:] - ff.mol_ptr[:-1]).long()
+        beta_atom = self.beta.repeat_interleave(sizes)
+        self.dtau = (self.dt / (beta_atom * float(friction))).contiguous()     # D dt
+
+    def _step_body(self, noise=None):
+        ff, st = self.ff, L.stream_ptr()
+        if noise is None:
+            noise = self.noise_buf
+        L.call("fmd_overdamped_step", L.ptr(self.pos), L.ptr(ff.forces), L.ptr(self.dtau), L.ptr(noise), self.seed, 0,
+               L.ptr(self.step_dev), self.node_offset, ff.N, st)
+        L.call("fmd_increment_u64", L.ptr(self.step_dev), st)
+        ff.compute(self.pos)
+        self.launches_per_step = ff.launches_per_eval + 2
 
 
 # ------------------------------------------------------------------------------------------------

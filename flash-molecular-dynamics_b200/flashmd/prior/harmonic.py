@@ -66,6 +66,7 @@ class HarmonicAngles(Harmonic):
 class HarmonicImpropers(Harmonic):
     name = "impropers"
     _order = 4
+    kernel_kind = 8
 
     def __init__(self, statistics) -> None:
         super().__init__(statistics, HarmonicImpropers.name, order=4)
@@ -83,6 +84,7 @@ class HarmonicAnglesRaw(Harmonic):
     """Harmonic in theta itself (radians) (reference prior/harmonic.py:267-300; there the constructor forgets Harmonic's
     `order` argument and raises - same signature here, working)."""
     name = "angles"
+    kernel_kind = 7
 
     def __init__(self, statistics, name="angles") -> None:
         super().__init__(statistics, HarmonicAnglesRaw.name, order=3)
@@ -101,7 +103,7 @@ class GeneralBonds(Harmonic):
     """Harmonic bonds registered under a caller-chosen name (several bond sets in one model; reference
     prior/harmonic.py:407-428)."""
     _order = 2
-    kernel_kind = None      # module path (not lowered to the fused step yet)
+    kernel_kind = 0
 
     def __init__(self, statistics, name) -> None:
         super().__init__(statistics, HarmonicBonds.name, order=GeneralBonds._order)
@@ -115,7 +117,7 @@ class GeneralBonds(Harmonic):
 class GeneralAngles(Harmonic):
     """Harmonic cos(angle) terms registered under a caller-chosen name (reference prior/harmonic.py:430-450)."""
     _order = 3
-    kernel_kind = None      # module path (not lowered to the fused step yet)
+    kernel_kind = 1
 
     def __init__(self, statistics, name) -> None:
         super().__init__(statistics, HarmonicAngles.name, order=GeneralAngles._order)
@@ -131,6 +133,7 @@ class ShiftedPeriodicHarmonicImpropers(Harmonic):
     and pi is subtracted, so the harmonic well sits at the discontinuity (reference prior/harmonic.py:327-405)."""
     name = "impropers"
     _order = 4
+    kernel_kind = 9
 
     def __init__(self, statistics) -> None:
         super().__init__(statistics, ShiftedPeriodicHarmonicImpropers.name, order=4)

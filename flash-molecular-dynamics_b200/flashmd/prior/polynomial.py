@@ -9,6 +9,16 @@ from .base import _Prior, type_table
 
 
 class Polynomial(_Prior):
+    @property
+    def kernel_kind(self):
+        """Fused-step kind (include/fmd_b200.h): polynomial in the bond length (order 2, degree <= 4; the lowering checks
+        that the attached feature function measures distances) or in cos(theta) (QuarticAngles, degree <= 6)."""
+        if isinstance(self, QuarticAngles):
+            return 5 if self.n_degs <= 6 else None
+        if self.order == 2 and self.n_degs <= 4 and hasattr(self, "compute_features"):
+            return 4
+        return None
+
     def __init__(self, statistics: Dict, name: str, order: Optional[int] = None, n_degs: int = 4) -> None:
         super().__init__()
         self.allowed_interaction_keys = list(statistics.keys())

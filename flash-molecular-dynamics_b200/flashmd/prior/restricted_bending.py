@@ -11,6 +11,7 @@ from .base import _Prior, type_table
 
 class RestrictedQuartic(_Prior):
     _fields = ("a", "b", "c", "d", "k", "v_0")
+    kernel_kind = 6
 
     def __init__(self, statistics: Dict, name: str = "angles") -> None:
         super().__init__()

@@ -133,7 +133,8 @@ class OverdampedSimulation(_Simulation):
     """Overdamped Langevin (Brownian) dynamics with the reference's exact update (simulation/langevin.py:315-420):
         D = 1 / (beta friction) per bead,  x += F D dt + sqrt(2 D dt) xi
     (the drift carries no extra beta - the reference's own convention, reproduced for parity).  Masses and velocities
-    are not used.  Module path (CPU or CUDA operators); pinned by tests/golden/integrators_n54_b4.npz."""
+    are not used.  CUDA fp32: the fused engine (fmd_overdamped_step + the force field, one CUDA graph per step); otherwise
+    the module path.  Pinned by tests/golden/integrators_n54_b4.npz."""
 
     def __init__(self, friction: float = 1.0, **kwargs: Any):
         super().__init__(**kwargs)
@@ -153,6 +154,29 @@ class OverdampedSimulation(_Simulation):
     def _set_up_simulation(self, overwrite: bool = False):
         super()._set_up_simulation(overwrite)
         self._noise_buffer = torch.empty((self.n_sims * self.n_atoms, self.n_dims), dtype=self.dtype, device=self.device)
+
+    # ------------------------------------------------------------------ fused path
+    def _build_engine(self, data):
+        if self.device.type != "cuda" or self.dtype != torch.float32 or getattr(self, "force_module_path", False):
+            return None
+        from ..engine import OverdampedEngine
+        from .lowering import NotLowerable, lower
+        try:
+            ff = lower(self.model, data, "w16a16" if self.gptq == "w16a16" else "fp32", self.exact_cutoff_grad)
+        except NotLowerable as err:
+            raise RuntimeError(f"the model cannot be lowered to the fused CUDA step ({err}); set "
+                               "`simulation.force_module_path = True` to run the PyTorch module path on purpose") from err
+        from .distributed import dist_info
+        rank, world = dist_info()
+        return OverdampedEngine(ff, data[POSITIONS_KEY], self.beta, self.dt, self.friction,
+                                seed=self.random_seed if self.random_seed is not None else 0, use_graph=True,
+                                noise_mode="buffer" if self.noise_source == "torch" else "philox",
+                                node_offset=rank * self.n_sims * self.n_atoms if world > 1 else 0)
+
+    def _engine_timestep(self, eng):
+        if eng.noise_buf is not None:
+            eng.noise_buf.normal_(generator=self.rng)
+        eng.step()
 
     def timestep(self, data, forces):
         noise = self._noise_buffer.normal_(generator=self.rng)

@@ -81,10 +81,24 @@ def prior_term(prior, data, device) -> PriorTerm:
     p = prior.data2parameters(data)
     f = lambda x: x.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
     kind = prior.kernel_kind
-    if kind in (L.PRIOR_BONDS, L.PRIOR_ANGLES):
+    if kind in (L.PRIOR_BONDS, L.PRIOR_ANGLES, L.PRIOR_RAW_ANGLES, L.PRIOR_IMPROPERS, L.PRIOR_SHIFTED_IMPROPERS):
         return PriorTerm(kind, mapping, mb, f(p["k"]), f(p["x0"]))
     if kind == L.PRIOR_DIHEDRALS:
         return PriorTerm(kind, mapping, mb, f(p["k1s"]), f(p["k2s"]), f(p["v_0"].flatten()), int(p["k1s"].shape[1]))
+    if kind in (L.PRIOR_POLY_BONDS, L.PRIOR_POLY_ANGLES):
+        if kind == L.PRIOR_POLY_BONDS:
+            from ..geometry import compute_distances
+            probe = torch.tensor([[0.0, 0.0, 0.0], [3.0, 4.0, 0.0]])
+            try:     # a Polynomial on a bond set must measure plain distances (users attach the feature function)
+                ok = float(prior.compute_features(probe, torch.tensor([[0], [1]]))) == 5.0
+            except Exception:  # noqa: BLE001
+                ok = False
+            if not ok:
+                raise NotLowerable("Polynomial prior of order 2 whose feature is not the bond length")
+        return PriorTerm(kind, mapping, mb, f(p["ks"]), None, f(p["v_0s"].flatten()))
+    if kind == L.PRIOR_RESTRICTED_ANGLES:
+        ks = torch.stack([p["a"], p["b"], p["c"], p["d"], p["k"]], 1)
+        return PriorTerm(kind, mapping, mb, f(ks), None, f(p["v_0"].flatten()))
     return PriorTerm(kind, mapping, mb, f(p["sigma"]))
 
 

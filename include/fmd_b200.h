@@ -274,6 +274,14 @@ int fmd_segment_sum(const float* e_atom, const int32_t* mol_ptr, int n_mols, flo
 #define FMD_PRIOR_ANGLES 1     /* k (cos(theta) - x0)^2 + V0   prior/harmonic.py:122-123 + internal_coordinates.py:140-170 */
 #define FMD_PRIOR_DIHEDRALS 2  /* v0 + sum_n k1_n sin(n phi) + k2_n cos(n phi)   prior/fourier_series.py:154-192 */
 #define FMD_PRIOR_REPULSION 3  /* (sigma / d)^6                 prior/repulsion.py:119-122 */
+#define FMD_PRIOR_POLY_BONDS 4 /* V0 + sum_{n=1..4} k_n d^n     prior/polynomial.py:13-186 (fmd_priors_csr only) */
+/* per-term form codes of the angle-like and improper-like tables of fmd_priors_csr */
+#define FMD_ANGLE_HARMONIC_COS 0   /* k (cos - x0)^2                           HarmonicAngles / GeneralAngles */
+#define FMD_ANGLE_POLY_COS 1       /* sum_{n=1..6} k_n cos^n                  QuarticAngles (prior/polynomial.py) */
+#define FMD_ANGLE_RESTRICTED 2     /* a c^4 + b c^3 + c c^2 + d c + k/sin^2   prior/restricted_bending.py:13-238 */
+#define FMD_ANGLE_HARMONIC_RAW 3   /* k (theta - x0)^2                        HarmonicAnglesRaw (prior/harmonic.py:267-300) */
+#define FMD_IMPROPER_HARMONIC 0    /* k (phi - x0)^2                          HarmonicImpropers (prior/harmonic.py:230-265) */
+#define FMD_IMPROPER_SHIFTED 1     /* k (x - x0)^2, x = (phi < 0 ? phi + 2 pi : phi) - pi   (prior/harmonic.py:327-405) */
 
 /* replaces: prior.forward + its torch.autograd.grad (models/gradients.py:265) for one condensed
  * prior term class. mapping [order, n_terms] int32 (row-major, rows = roles), mapping_batch
@@ -292,16 +300,22 @@ int fmd_prior_energy_forces(int kind, const float* pos, const int32_t* mapping, 
  * :265; simulation/specialize_prior.py:112-207).
  *   pair_ptr [n_nodes+1], pair_ent [n_pair_inc] of 16-byte records {other | kind<<28, p0, p1, p2}
  *     (kind FMD_PRIOR_BONDS: k, x0, V0; FMD_PRIOR_REPULSION: sigma, -, -), every pair listed under BOTH beads;
- *     with pair_tab != NULL the records are 8 bytes {other | kind<<28, id} and (p0, p1, p2, -) = pair_tab[4 id ..]
- *     (deduplicated parameter table, float4 per entry: halves the largest HBM stream outside the edge kernels);
- *   mb_ptr [n_nodes+1], mb_ent [n_mb_inc] = term | role<<28 | is_dihedral<<30, every term under each of its beads;
- *   ang_map [3,n_ang], dih_map [4,n_dih] int32 + flat parameter vectors (ang_v0 / dih_v0 nullable).
+ *     with pair_tab != NULL the records are 8 bytes {other | kind<<28, id} and the parameters are the 8 floats
+ *     pair_tab[8 id ..] (deduplicated table: halves the largest HBM stream outside the edge kernels):
+ *     (p0, p1, p2, p3 | p4, -, -, -); FMD_PRIOR_POLY_BONDS (packed records only): k1..k4 | V0;
+ *   mb_ptr [n_nodes+1], mb_ent [n_mb_inc] = term | role<<28 | table<<30 (0 angle-like, 1 Fourier dihedral,
+ *     2 improper-like), every term under each of its beads;
+ *   ang_map [3,n_ang] + ang_par [n_ang,8] = {p0..p5, V0, form as int bits}: HARMONIC_COS (k, x0), POLY_COS (k1..k6),
+ *     RESTRICTED (a, b, c, d, k), HARMONIC_RAW (k, x0) - several angle prior classes share the one table;
+ *   dih_map [4,n_dih] + k1, k2 [n_dih,n_degs], v0 [n_dih] | NULL;
+ *   imp_map [4,n_imp] + imp_par [n_imp,4] = {k, x0, V0, form}.
  * Outputs: e_atom [n_nodes] = the bead's share of its terms' energies (sum per molecule with
  * fmd_segment_sum), forces [n_nodes,3] written (accumulate_forces == 0) or added to. Any group may be NULL. */
 int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair_ptr, const void* pair_ent, const float* pair_tab,
-                   const int32_t* mb_ptr, const int32_t* mb_ent, const int32_t* ang_map, int n_ang, const float* ang_k, const float* ang_x0,
-                   const float* ang_v0, const int32_t* dih_map, int n_dih, const float* dih_k1, const float* dih_k2,
-                   const float* dih_v0, int n_degs, float* e_atom, float* forces, int accumulate_forces, void* stream);
+                   const int32_t* mb_ptr, const int32_t* mb_ent, const int32_t* ang_map, int n_ang, const float* ang_par,
+                   const int32_t* dih_map, int n_dih, const float* dih_k1, const float* dih_k2, const float* dih_v0,
+                   int n_degs, const int32_t* imp_map, int n_imp, const float* imp_par, float* e_atom, float* forces,
+                   int accumulate_forces, void* stream);
 
 /* ---------------------------------------------------------------- integrator ---------------- */
 
@@ -314,6 +328,11 @@ int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair_ptr, const
 int fmd_baoab_pre(float* pos, float* vel, const float* forces, const float* inv_mass, const float* noise_std,
                   const float* noise, uint64_t seed, uint64_t step, const uint64_t* step_dev, uint64_t node_offset,
                   int n_nodes, float dt, float vscale, float noisescale, void* stream);
+
+/* replaces: OverdampedSimulation.timestep (simulation/langevin.py:361-414): x += F dtau + sqrt(2 dtau) xi in place,
+ * dtau [n_nodes] = D dt with the reference's D = 1 / (beta friction) per bead. Noise as in fmd_baoab_pre. */
+int fmd_overdamped_step(float* pos, const float* forces, const float* dtau, const float* noise, uint64_t seed,
+                        uint64_t step, const uint64_t* step_dev, uint64_t node_offset, int n_nodes, void* stream);
 
 /* *counter += 1 on the stream (keeps the Philox step counter on the device so a captured CUDA
  * graph of the whole step can be replayed; fmd_baoab_pre adds *step_dev to `step`). */

@@ -133,3 +133,39 @@ def dropin_model_from_golden(g, embedding_size=None):
                                               atom_types=torch.from_numpy(g["sys.atom_types"]),
                                               masses=torch.from_numpy(g["sys.masses"]), neighborlist=nls))
     return model, schnet, configs
+
+
+def extra_prior_objects():
+    """The prior classes beyond the benchmark's four, built on the golden 4 x 54-bead system exactly like
+    oracle/make_golden.py --extra-priors builds the reference objects: {name: (prior, mapping, order)} and the system."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT_DIR, "oracle"))
+    import extra_prior_stats as X
+    from flashmd import synthetic
+    from flashmd.geometry import compute_distances
+    from flashmd.prior import (GeneralAngles, GeneralBonds, Polynomial, QuarticAngles, RestrictedQuartic,
+                               ShiftedPeriodicHarmonicImpropers)
+    system = synthetic.synthetic_system(4, 54, seed=0, target_degree=30.0)
+    ty = system["atom_types"]
+    kb, ka, kd = X.type_keys(ty, system["bonds"]), X.type_keys(ty, system["angles"]), X.type_keys(ty, system["dihedrals"])
+    poly = Polynomial(X.polynomial_stats(kb), "poly_bonds", order=2, n_degs=4)
+    poly.compute_features = staticmethod(compute_distances)
+    priors = {
+        "gbonds": (GeneralBonds(X.harmonic_stats(kb, 3.6, 4.0), "gbonds"), system["bonds"], 2),
+        "gangles": (GeneralAngles(X.harmonic_stats(ka, -0.6, 0.2), "gangles"), system["angles"], 3),
+        "poly_bonds": (poly, system["bonds"], 2),
+        "quartic_angles": (QuarticAngles(X.polynomial_stats(ka), name="quartic_angles"), system["angles"], 3),
+        "restricted": (RestrictedQuartic(X.restricted_quartic_stats(ka), name="restricted"), system["angles"], 3),
+        "shifted_impropers": (ShiftedPeriodicHarmonicImpropers(X.harmonic_stats(kd, -0.5, 0.5)), system["dihedrals"], 4),
+    }
+    return priors, system
+
+
+def extra_prior_configs(prior, mapping, order, system):
+    from flashmd.data import AtomicData
+    from flashmd.neighbor_list import make_neighbor_list
+    ty = system["atom_types"]
+    return [AtomicData.from_points(pos=torch.from_numpy(system["pos"][b].copy()), atom_types=torch.from_numpy(ty),
+                                   masses=torch.from_numpy(system["masses"]),
+                                   neighborlist={prior.name: make_neighbor_list(prior.name, order, torch.from_numpy(mapping))})
+            for b in range(4)]

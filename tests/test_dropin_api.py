@@ -219,36 +219,13 @@ def test_extra_prior_classes_match_reference():
     reference (tests/golden/extra_priors_n54_b4.npz, oracle/make_golden.py --extra-priors); statistics tables shared
     through oracle/extra_prior_stats.py.  (HarmonicAnglesRaw and HarmonicImpropers cannot run in the reference itself:
     harmonic.py:287 / :313.)"""
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
-    import extra_prior_stats as X
-    from flashmd import synthetic
-    from flashmd.data import AtomicData
-    from flashmd.geometry import compute_distances
+    from helpers import extra_prior_configs, extra_prior_objects
     from flashmd.models import GradientsOut, SumOut
-    from flashmd.neighbor_list import make_neighbor_list
-    from flashmd.prior import (GeneralAngles, GeneralBonds, Polynomial, QuarticAngles, RestrictedQuartic,
-                               ShiftedPeriodicHarmonicImpropers)
     from flashmd.simulation import LangevinSimulation
     t = load_golden("extra_priors_n54_b4.npz")
-    system = synthetic.synthetic_system(4, 54, seed=0, target_degree=30.0)
-    ty = system["atom_types"]
-    kb, ka, kd = X.type_keys(ty, system["bonds"]), X.type_keys(ty, system["angles"]), X.type_keys(ty, system["dihedrals"])
-    poly = Polynomial(X.polynomial_stats(kb), "poly_bonds", order=2, n_degs=4)
-    poly.compute_features = staticmethod(compute_distances)
-    priors = {
-        "gbonds": (GeneralBonds(X.harmonic_stats(kb, 3.6, 4.0), "gbonds"), system["bonds"], 2),
-        "gangles": (GeneralAngles(X.harmonic_stats(ka, -0.6, 0.2), "gangles"), system["angles"], 3),
-        "poly_bonds": (poly, system["bonds"], 2),
-        "quartic_angles": (QuarticAngles(X.polynomial_stats(ka), name="quartic_angles"), system["angles"], 3),
-        "restricted": (RestrictedQuartic(X.restricted_quartic_stats(ka), name="restricted"), system["angles"], 3),
-        "shifted_impropers": (ShiftedPeriodicHarmonicImpropers(X.harmonic_stats(kd, -0.5, 0.5)), system["dihedrals"], 4),
-    }
+    priors, system = extra_prior_objects()
     for name, (prior, mapping, order) in priors.items():
-        configs = [AtomicData.from_points(pos=torch.from_numpy(system["pos"][b].copy()), atom_types=torch.from_numpy(ty),
-                                          masses=torch.from_numpy(system["masses"]),
-                                          neighborlist={prior.name: make_neighbor_list(prior.name, order, torch.from_numpy(mapping))})
-                   for b in range(4)]
+        configs = extra_prior_configs(prior, mapping, order, system)
         model = SumOut(torch.nn.ModuleDict({prior.name: GradientsOut(prior)}))
         for dt, tag, tol in ((torch.float64, "ref64", 1e-12), (torch.float32, "ref32", 2e-5)):
             data = LangevinSimulation.collate(configs)

@@ -553,6 +553,36 @@ def test_edge_capacity_and_large_batch_properties():
     assert rel_l2(f[:n].cpu(), f0) < 1e-5 and rel_l2(e[:1].cpu(), e0) < 1e-5
 
 
+def test_cfg5_shape_500_beads_5_blocks_vs_oracle():
+    """BASELINE config 5's shape at a batch the CPU oracle finishes in seconds: 2 x 500 beads, 5 interaction blocks,
+    ~55 neighbours per bead.  fp32 path 1e-5 against the fp64 oracle, W16A16 path (fused tcgen05 kernels) 1e-2 against the
+    oracle's W16A16 model (itself pinned against the reference's Triton W16A16 run), neighbour list bit-exact."""
+    from flashmd import synthetic
+    from flashmd.engine import ForceField, SchNetWeights, random_schnet_tensors
+    B, n, L_ = 2, 500, 5
+    sysd = synthetic.synthetic_system(B, n, seed=4)
+    pos = torch.from_numpy(sysd["pos"]).reshape(B * n, 3)
+    types = torch.from_numpy(sysd["atom_types"]).repeat(B)
+    ptr = np.arange(B + 1) * n
+    tensors = random_schnet_tensors(12, num_blocks=L_)
+    w = SchNetWeights.from_flat(tensors, sysd["cutoff"], 50, DEV)
+    P = O.SchNetParams({k: (v if v is None else v.clone()) for k, v in tensors.items()} | {"out2_b": None}, L_, 3,
+                       sysd["cutoff"], 50)
+    batch = torch.arange(B).repeat_interleave(n)
+    ei = torch.from_numpy(O.radius_graph(pos.numpy(), ptr, sysd["cutoff"]))
+    e64, f64 = O.schnet_energy_forces(P.to(torch.float64), pos.double(), types, batch, B, ei)
+    e16, f16 = O.schnet_energy_forces(P, pos, types, batch, B, ei, precision="w16a16")
+    for prec, (e_ref, f_ref), tol in (("fp32", (e64, f64), 1e-5), ("w16a16", (e16, f16), 1e-2)):
+        ff = ForceField(w, [], types.to(DEV), torch.from_numpy(ptr).to(DEV), precision=prec)
+        e, f = ff.compute(pos.to(DEV).contiguous())
+        E = ff.num_edges()
+        assert np.array_equal(torch.stack([ff.src[:E], ff.dst[:E]]).cpu().numpy().astype(np.int64), ei.numpy())
+        assert rel_l2(f.cpu(), f_ref) < tol, (prec, rel_l2(f.cpu(), f_ref))
+        assert rel_l2(e.cpu(), e_ref) < tol, (prec, rel_l2(e.cpu(), e_ref))
+        if prec == "w16a16":
+            assert ff.fused_tc and rel_l2(f.cpu(), f64) < 1e-2
+
+
 # ----------------------------------------------------------------------------- integrator
 def test_langevin_trajectory_vs_reference_golden():
     """10 BAOAB steps replayed with the reference's own noise (simulation/langevin.py:101-179)."""
@@ -568,7 +598,9 @@ def test_langevin_trajectory_vs_reference_golden():
     for s in range(t["noise"].shape[0]):
         eng.step(noise=torch.from_numpy(t["noise"][s]).to(DEV).contiguous())
         assert rel_l2(eng.pos.view(B, n, 3).cpu(), t["coords"][:, s]) < 1e-6
-        assert rel_l2(ff.forces.view(B, n, 3).cpu(), t["forces"][:, s]) < 5e-4
+        # the reference's own fp32 trajectory forces carry the cancellation noise of the stiff bond terms (k (d - x0)^2 with
+        # d - x0 << d): the CPU oracle agrees with them to 2e-4 (tests/test_oracle_golden.py), the same bar holds here
+        assert rel_l2(ff.forces.view(B, n, 3).cpu(), t["forces"][:, s]) < 2e-4
         assert rel_l2(ff.energy.cpu(), t["potential"][:, s]) < 1e-5
         assert rel_l2(eng.ke.cpu(), t["kinetic"][:, s]) < 1e-5
 

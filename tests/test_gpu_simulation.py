@@ -334,3 +334,72 @@ def test_nccl_sharded_exchange_two_gpus():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "sharded PTSimulation ok on all ranks: True" in r.stdout
+
+
+def test_extra_prior_classes_run_on_the_fused_step():
+    """GeneralBonds / GeneralAngles / Polynomial (bond lengths) / QuarticAngles / RestrictedQuartic / shifted impropers are
+    lowered to the owner-computes prior kernel (one launch for all prior classes) instead of dropping the model to the
+    module path; energies and forces against the UNMODIFIED reference (tests/golden/extra_priors_n54_b4.npz), alone and
+    all six together next to the benchmark's four."""
+    from helpers import extra_prior_configs, extra_prior_objects
+    from flashmd.models import GradientsOut, SumOut
+    from flashmd.simulation import LangevinSimulation
+    from flashmd.simulation.lowering import lower
+    t = load_golden("extra_priors_n54_b4.npz")
+    priors, system = extra_prior_objects()
+    e_sum, f_sum, nls = 0.0, 0.0, {}
+    for name, (prior, mapping, order) in priors.items():
+        configs = extra_prior_configs(prior, mapping, order, system)
+        data = LangevinSimulation.collate(configs).to(DEV)
+        model = SumOut(torch.nn.ModuleDict({prior.name: GradientsOut(prior)})).to(DEV)
+        ff = lower(model, data, "fp32")
+        e, f = ff.compute(data.pos.float().contiguous())
+        for what, val in (("energy", e), ("forces", f)):
+            r32, r64 = t[f"ref32.{name}.{what}"], t[f"ref64.{name}.{what}"]
+            tol = max(1e-5, 2.0 * rel_l2(r32, r64))
+            assert rel_l2(val.cpu(), r64) < tol, (name, what, rel_l2(val.cpu(), r64), tol)
+        e_sum, f_sum = e_sum + t[f"ref64.{name}.energy"], f_sum + t[f"ref64.{name}.forces"]
+        nls[prior.name] = (mapping, order)
+    # all six in ONE model (two angle-like classes share the angle table, impropers next to nothing else)
+    from flashmd.data import AtomicData
+    from flashmd.neighbor_list import make_neighbor_list
+    ty = system["atom_types"]
+    configs = [AtomicData.from_points(pos=torch.from_numpy(system["pos"][b].copy()), atom_types=torch.from_numpy(ty),
+                                      masses=torch.from_numpy(system["masses"]),
+                                      neighborlist={nm: make_neighbor_list(nm, o, torch.from_numpy(m)) for nm, (m, o) in nls.items()})
+               for b in range(4)]
+    data = LangevinSimulation.collate(configs).to(DEV)
+    model = SumOut(torch.nn.ModuleDict({p.name: GradientsOut(p) for p, _, _ in priors.values()})).to(DEV)
+    ff = lower(model, data, "fp32")
+    e, f = ff.compute(data.pos.float().contiguous())
+    assert rel_l2(e.cpu(), e_sum) < 3e-5 and rel_l2(f.cpu(), f_sum) < 3e-5
+
+
+def test_overdamped_integrator_on_the_fused_engine(tmp_path):
+    """OverdampedSimulation's update (reference simulation/langevin.py:361-414: D = 1 / (beta friction), x += F D dt +
+    sqrt(2 D dt) xi) on the fused engine, step for step against the UNMODIFIED reference's trajectory
+    (tests/golden/integrators_n54_b4.npz) with the reference's own noise stream (torch.Generator(seed) on the CPU);
+    then through OverdampedSimulation itself (Philox noise, CUDA graph): fused path, finite, diffusing."""
+    from flashmd.engine import OverdampedEngine
+    from flashmd.simulation import OverdampedSimulation
+    from test_gpu_parity import _engine_from_golden
+    g = load_golden("schnet_n54_b4.npz")
+    t = load_golden("integrators_n54_b4.npz")
+    _, dt_od, fr_od, beta, seed, _ = (float(v) for v in t["params"])
+    B, n = 4, 54
+    ff, pos = _engine_from_golden(g, "fp32", priors=True)
+    eng = OverdampedEngine(ff, pos, torch.full((B,), beta), dt_od, fr_od, use_graph=False)
+    gen = torch.Generator(device="cpu").manual_seed(int(seed))
+    for s_ in range(t["overdamped.coords"].shape[1]):
+        noise = torch.empty((B * n, 3)).normal_(generator=gen)
+        eng.step(noise=noise.to(DEV).contiguous())
+        assert rel_l2(eng.pos.view(B, n, 3).cpu(), t["overdamped.coords"][:, s_]) < 1e-5, s_
+        assert rel_l2(ff.energy.cpu(), t["overdamped.potential"][:, s_]) < 1e-4, s_
+    model, _, configs = dropin_model_from_golden(g)
+    sim = OverdampedSimulation(dt=dt_od, friction=fr_od, n_timesteps=200, save_interval=20, export_interval=200,
+                               save_energies=True, random_seed=3, device=DEV, filename="od", output_dir=str(tmp_path))
+    sim.attach_model_and_configurations(model, configs, beta=beta)
+    sim.simulate()
+    assert sim.get_throughput_metrics()["path"] == "fused-engine"
+    x = np.load(tmp_path / "od_coords_0000.npy")           # [n_sims, frames, n_atoms, 3]
+    assert x.shape == (4, 10, 54, 3) and np.isfinite(x).all() and np.abs(x[:, -1] - x[:, 0]).max() > 1e-2
