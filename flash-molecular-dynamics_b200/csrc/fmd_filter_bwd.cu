@@ -20,17 +20,20 @@
 // One persistent CTA per SM, 23 warps (every SIMT role is one serial dependency chain per tile, so the roles - not the
 // issue slots - bound the tile period: five groups of four warps instead of four):
 //   P  warps 0-3    metadata + radial-basis row
-//   G  warps 4-7    rows a[nbr_e,:] (fp16, 256 B) are copied by cp.async STRAIGHT INTO the swizzled K-major operand
-//                   buffer of MMA3 (16-byte chunks land at their swizzled positions), one tile ahead; thread e then
-//                   multiplies ITS row in place by g_m[own_e,:] with packed HMUL2 (16-byte shared-memory vectors, the
-//                   g_m row is a broadcast 16-byte global load): 0.9 instructions per element instead of the ~5 of a
-//                   per-thread-per-feature gather, and no L2 latency in the role's critical path
+//   G  warps 4-7    rows a[nbr_e,:] (fp16, 256 B) are staged one tile ahead with cp.async (two full rows per instruction,
+//                   coalesced; each warp stages and later reads only ITS 32 rows: cp.async groups, no barrier); thread e
+//                   reads ITS row with 16-byte shared-memory loads, multiplies by g_m[own_e,:] with packed HMUL2 (the g_m
+//                   row is a broadcast 16-byte global load) and writes the fp16 row with tcgen05.st into TENSOR MEMORY,
+//                   where MMA3 reads it as its A operand.  (The kernel is bound by the shared-memory / L1TEX pipe - ncu:
+//                   77 % of peak with the operand multiplied in place in shared memory and read from there by the MMA;
+//                   per-lane row loads straight from global cost as much in L1TEX: 32 sectors per instruction.)
 //   A  warps 8-11   D1^T -> tanh -> t row (stash)
 //   B  warps 12-15  D3^T -> g_t row (in place over t) + in-thread cut-off term sum
 //   E4 warps 16-19  D4 -> g_d (lags up to 4 tiles: D4 is quadruple-buffered)
 //   M  warps 20-22  one MMA-issuer thread per GEMM (an issuer blocks in program order on its mbarriers)
 // Software arrivals on the mbarriers are one per warp (lane 0 after __syncwarp).
-// TMEM: D13[2] (D1^T then D3^T of the same tile) at s*128, D4[4] (64 columns) at 256 + q*64.
+// TMEM: D13[2] (D1^T then D3^T of the same tile) at s*128, D4[2] (64 columns) at 256 + q*64, gW0[2] (fp16 pairs, 64 columns)
+// at 384 + s*64.
 #include "fmd_filter_shared.cuh"
 
 using namespace fmd;
@@ -41,25 +44,29 @@ namespace {
 
 constexpr int BWD_THREADS = 23 * 32;   // 6 warps on three SM sub-partitions: 16384 / (6 * 32) -> 80 registers per thread
 constexpr int META_STAGES = 4;
-constexpr int D4_STAGES = 4;   // D4 (64 columns) is quadruple-buffered so that e4 may lag 4 tiles behind produce
+constexpr int D4_STAGES = 2;
+constexpr uint32_t TM_D4 = 256, TM_GW = 384;   // tensor-memory column bases
 
 constexpr uint32_t BO_WF0 = 0;
 constexpr uint32_t BO_WF1 = BO_WF0 + 128 * 128;
 constexpr uint32_t BO_RBF = BO_WF1 + 2 * 128 * 128;          // 2 x 16 KB
-constexpr uint32_t BO_OP = BO_RBF + 2 * 128 * 128;           // 2 x 32 KB: gW0 [e][f], K-major A operand of MMA3
-constexpr uint32_t BO_ST = BO_OP + 2 * 2 * 128 * 128;        // 2 x 32 KB: t stash, overwritten in place by g_t (A operand of MMA4)
+constexpr int APITCH = 272;                                   // bytes per staged row: 256 + 16 (conflict-free 16-byte row-per-lane reads)
+constexpr uint32_t BO_AS = BO_RBF + 2 * 128 * 128;           // 2 x 34 KB: staged rows a[nbr_e,:]
+constexpr uint32_t BO_ST = BO_AS + 2 * TILE * APITCH;        // 2 x 32 KB: t stash, overwritten in place by g_t (A operand of MMA4)
 constexpr uint32_t BO_META = BO_ST + 2 * 2 * 128 * 128;      // 4 x 1 KB: {byte offset nbr * 256, C(d_e)}
 constexpr uint32_t BO_OWN = BO_META + META_STAGES * TILE * 8;  // 4 x 512 B
 constexpr uint32_t BO_RED = BO_OWN + META_STAGES * TILE * 4;   // 4 x [128] floats: cut-off term sum per edge
 constexpr uint32_t BO_CEN = BO_RED + 4 * TILE * 4;
 constexpr uint32_t BO_BAR = BO_CEN + RP * 4;
-constexpr uint32_t BSMEM = BO_BAR + 40 * 8 + 16;
+constexpr uint32_t BSMEM = BO_BAR + 48 * 8 + 16;
 constexpr uint32_t BSMEM_ALLOC = BSMEM + 1024;
 static_assert(BSMEM_ALLOC <= 232448, "backward kernel exceeds the 227 KB shared-memory limit");
 
 enum { C_RBF_FULL = 0, C_RBF_EMPTY = 2, C_D1_FULL = 4, C_D1_EMPTY = 6, C_GW_FULL = 8, C_D3_FULL = 10, C_D3_EMPTY = 12,
        C_GT_FULL = 14, C_OP_EMPTY = 16, C_D4_FULL = 18, C_D4_EMPTY = 22, C_META_FULL = 26, C_META_EMPTY = 30,
-       C_ST_EMPTY = 34, C_ST_FULL = 36, C_COUNT = 38 };
+       C_ST_EMPTY = 34, C_ST_FULL = 36,
+       // second halves (columns 64-127 of the tile's 128 filter columns): D1 drained / t written / D3 ready
+       C_D1E_HI = 38, C_STF_HI = 40, C_D3F_HI = 42, C_COUNT = 44 };
 
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -75,6 +82,40 @@ template <bool kTrace>
 __device__ __forceinline__ void trace_stamp(unsigned long long* trace, int role, int tile, int k, bool leader) {
   if (kTrace) {
     if (blockIdx.x == 0 && leader && tile < 64) trace[(role * 64 + tile) * 3 + k] = (unsigned long long)clock64();
+  }
+}
+
+// One 32-column chunk of  D3^T -> g_t  for this thread's edge row: g_t = D3 * C (1 - t^2) written in place over t (the
+// K-major A operand of MMA4), and (exact mode) the running sum_j t_j D3_j of the cut-off term.
+template <bool kExact>
+__device__ __forceinline__ void gt_chunk(uint32_t d3, uint8_t* sT, uint32_t x7, uint32_t cut2, uint32_t ncut2, float& usum,
+                                         int c) {
+  uint32_t r[32];
+  tmem_ld32(d3 + c * 32, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = c * 4 + q;
+    uint4* slot = reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + ((((uint32_t)chunk & 7u) << 4) ^ x7));
+    const uint4 tq = *slot;
+    const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
+    uint32_t p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = q * 8 + 2 * u;
+      // D3 pair rounded to fp16 once (it is an fp16 operand after the next multiply anyway)
+      const uint32_t dh = pack_half2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
+      if (kExact) {   // sum_j t_j D3_j: fp16 x fp16 products are exact in fp32, fp32 accumulate (FHFMA)
+        asm("{\n\t.reg .b16 tl, th, dl, dh;\n\tmov.b32 {tl, th}, %1;\n\tmov.b32 {dl, dh}, %2;\n\t"
+            "fma.rn.f32.f16 %0, tl, dl, %0;\n\tfma.rn.f32.f16 %0, th, dh, %0;\n\t}" : "+f"(usum) : "r"(tw[u]), "r"(dh));
+      }
+      // the factor C (1 - t^2) as cut - (t cut) t in packed half arithmetic
+      uint32_t wgt;
+      asm("{\n\t.reg .b32 tc;\n\tmul.rn.f16x2 tc, %1, %3;\n\tfma.rn.f16x2 %0, tc, %1, %2;\n\t}"
+          : "=r"(wgt) : "r"(tw[u]), "r"(cut2), "r"(ncut2));
+      p[u] = hmul2_u32(dh, wgt);
+    }
+    *slot = make_uint4(p[0], p[1], p[2], p[3]);
   }
 }
 
@@ -94,7 +135,7 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* sCen = reinterpret_cast<float*>(smem + BO_CEN);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + BO_BAR + 40 * 8);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + BO_BAR + 48 * 8);
   auto bar = [&](int i) { return sbase + BO_BAR + 8u * (uint32_t)i; };
 
   const int E = min(capacity, n_edges_dev ? *n_edges_dev : capacity);
@@ -124,6 +165,9 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
       mbar_init(bar(C_OP_EMPTY + i), 1);
       mbar_init(bar(C_ST_EMPTY + i), 1);
       mbar_init(bar(C_ST_FULL + i), 4);
+      mbar_init(bar(C_D1E_HI + i), 4);
+      mbar_init(bar(C_STF_HI + i), 4);
+      mbar_init(bar(C_D3F_HI + i), 1);
     }
     for (int i = 0; i < D4_STAGES; ++i) {
       mbar_init(bar(C_D4_FULL + i), 1);
@@ -137,7 +181,7 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc(sbase + BO_BAR + 40 * 8, 512);
+    tmem_alloc(sbase + BO_BAR + 48 * 8, 512);
   }
   fence_async_smem();
   fence_before_sync();
@@ -216,22 +260,17 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
     }
   } else if (warp < 8) {
     // =========================================================== G: gW0 rows (thread = edge row e of the tile)
-    const int w = warp - 4;
+    const int w = warp & 3;
     const int e = w * 32 + lane;
-    const uint32_t rowoff = (uint32_t)((e >> 3) * 1024 + (e & 7) * 128), x7 = (uint32_t)(e & 7) << 4;
+    const uint32_t lane_sel = (uint32_t)(w * 32) << 16;
     const int sub = lane >> 4, ch = lane & 15;                   // copy instruction: two rows x sixteen 16-byte chunks
     const uint8_t* asrc = reinterpret_cast<const uint8_t*>(a) + ch * 16;
-    // the warp copies ITS 32 rows (2 per instruction) -> only this warp reads them back: cp.async groups + __syncwarp suffice
     auto issue_rows = [&](int i) {
-      const int s = i & 1, ms = i & (META_STAGES - 1);
+      const int ms = i & (META_STAGES - 1);
       const uint2* sMeta = reinterpret_cast<const uint2*>(smem + BO_META + ms * TILE * 8) + w * 32 + sub;
-      const uint32_t op = sbase + BO_OP + (uint32_t)(s * (2 * 128 * 128) + (ch >> 3) * (128 * 128));
+      const uint32_t dst = sbase + BO_AS + (uint32_t)((i & 1) * (TILE * APITCH) + (w * 32 + sub) * APITCH + ch * 16);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int row = w * 32 + 2 * q + sub;
-        const uint32_t dst = op + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128) + ((((uint32_t)ch & 7u) ^ ((uint32_t)row & 7u)) << 4);
-        cp_async16(dst, asrc + sMeta[2 * q].x);
-      }
+      for (int q = 0; q < 16; ++q) cp_async16(dst + (uint32_t)(2 * q * APITCH), asrc + sMeta[2 * q].x);
     };
     if (n_my > 0) {
       mbar_wait_guard(bar(C_META_FULL + 0), 0);
@@ -241,35 +280,36 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
     for (int i = 0; i < n_my; ++i) {
       const int s = i & 1, ms = i & (META_STAGES - 1);
       TR(2, i, 0, e == 0);
+      // next tile's rows first: their staging buffer was read by this warp one iteration ago (nothing else touches it)
       if (i + 1 < n_my) {
         mbar_wait_guard(bar(C_META_FULL + ((i + 1) & (META_STAGES - 1))), ((i + 1) / META_STAGES) & 1);
-        if (i >= 1) mbar_wait_guard(bar(C_OP_EMPTY + ((i + 1) & 1)), ((i - 1) >> 1) & 1);   // MMA3(i-1) has read that buffer
         issue_rows(i + 1);
       }
       cp_async_commit();
+      if (i >= 2) mbar_wait_guard(bar(C_OP_EMPTY + s), ((i - 2) >> 1) & 1);   // MMA3(i-2) has read gW0[s] (tensor memory)
+      fence_after_sync();
       cp_async_wait<1>();          // the rows of tile i have landed ...
       __syncwarp();                // ... for every lane of this warp
       TR(2, i, 1, e == 0);
       const int own = reinterpret_cast<const int*>(smem + BO_OWN + ms * TILE * 4)[e];
       const uint4* gmrow = reinterpret_cast<const uint4*>(g_m + (size_t)own * NF);
-      uint8_t* op = smem + BO_OP + s * (2 * 128 * 128) + rowoff;
+      const uint4* arow = reinterpret_cast<const uint4*>(smem + BO_AS + s * (TILE * APITCH) + e * APITCH);
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-        uint4 gv[8];
+      for (int q = 0; q < 4; ++q) {
+        uint32_t r[16];
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) gv[cc] = __ldg(gmrow + kb * 8 + cc);
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-          uint4* slot = reinterpret_cast<uint4*>(op + kb * (128 * 128) + (((uint32_t)cc << 4) ^ x7));   // logical chunk cc
-          uint4 av = *slot;
-          av.x = hmul2_u32(av.x, gv[cc].x);
-          av.y = hmul2_u32(av.y, gv[cc].y);
-          av.z = hmul2_u32(av.z, gv[cc].z);
-          av.w = hmul2_u32(av.w, gv[cc].w);
-          *slot = av;
+        for (int c = 0; c < 4; ++c) {
+          const uint4 av = arow[q * 4 + c];
+          const uint4 gv = __ldg(gmrow + q * 4 + c);
+          r[4 * c + 0] = hmul2_u32(av.x, gv.x);
+          r[4 * c + 1] = hmul2_u32(av.y, gv.y);
+          r[4 * c + 2] = hmul2_u32(av.z, gv.z);
+          r[4 * c + 3] = hmul2_u32(av.w, gv.w);
         }
+        tmem_st16(tmem + TM_GW + s * 64 + lane_sel + q * 16, r);
       }
-      fence_async_smem();
+      tmem_st_wait();
+      fence_before_sync();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(C_GW_FULL + s));
@@ -305,18 +345,23 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
               make_uint4(p[0], p[1], p[2], p[3]);
         }
       };
+      // The accumulator is handed on in two 64-column halves: MMA3 overwrites D1 with D3 half by half and B starts on the
+      // first half while this role still works on the second (D1 and D3 share the buffer, so the chain
+      // MMA1 -> A -> MMA3 -> B per buffer was the critical path of the kernel)
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t ra[32];
         tmem_ld32(d1 + c * 32, ra);
         tmem_ld_wait();
         process(ra, c);
-      }
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(C_D1_EMPTY + s));
-        mbar_arrive(bar(C_ST_FULL + s));
+        if (c & 1) {
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar((c == 1 ? C_D1_EMPTY : C_D1E_HI) + s));
+            mbar_arrive(bar((c == 1 ? C_ST_FULL : C_STF_HI) + s));
+          }
+        }
       }
       TR(4, i, 2, e == 0);
     }
@@ -342,38 +387,14 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
       const uint32_t cut2 = pack_half2(cut, cut), ncut2 = pack_half2(-cut, -cut);
       float usum = 0.f;
       const uint32_t d3 = tmem + s * 128 + lane_sel;
-      auto process = [&](const uint32_t (&r)[32], int c) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = c * 4 + q;
-          uint4* slot = reinterpret_cast<uint4*>(sT + (chunk >> 3) * (128 * 128) + ((((uint32_t)chunk & 7u) << 4) ^ x7));
-          const uint4 tq = *slot;
-          const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
-          uint32_t p[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int k = q * 8 + 2 * u;
-            // D3 pair rounded to fp16 once (it is an fp16 operand after the next multiply anyway)
-            const uint32_t dh = pack_half2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
-            if (kExact) {   // sum_j t_j D3_j: fp16 x fp16 products are exact in fp32, fp32 accumulate (FHFMA)
-              asm("{\n\t.reg .b16 tl, th, dl, dh;\n\tmov.b32 {tl, th}, %1;\n\tmov.b32 {dl, dh}, %2;\n\t"
-                  "fma.rn.f32.f16 %0, tl, dl, %0;\n\tfma.rn.f32.f16 %0, th, dh, %0;\n\t}" : "+f"(usum) : "r"(tw[u]), "r"(dh));
-            }
-            // g_t = D3 * C (1 - t^2), the factor as cut - (t cut) t in packed half arithmetic
-            uint32_t wgt;
-            asm("{\n\t.reg .b32 tc;\n\tmul.rn.f16x2 tc, %1, %3;\n\tfma.rn.f16x2 %0, tc, %1, %2;\n\t}"
-                : "=r"(wgt) : "r"(tw[u]), "r"(cut2), "r"(ncut2));
-            p[u] = hmul2_u32(dh, wgt);
-          }
-          *slot = make_uint4(p[0], p[1], p[2], p[3]);
-        }
-      };
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        uint32_t ra[32];
-        tmem_ld32(d3 + c * 32, ra);
-        tmem_ld_wait();
-        process(ra, c);
+        if (c == 2) {
+          mbar_wait_guard(bar(C_STF_HI + s), ph);
+          mbar_wait_guard(bar(C_D3F_HI + s), ph);
+          fence_after_sync();
+        }
+        gt_chunk<kExact>(d3, sT, x7, cut2, ncut2, usum, c);
       }
       if (kExact) red[j] = usum;
       fence_before_sync();
@@ -426,7 +447,7 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
       for (int c = 0; c < 64; c += 16) {
         if (c >= R) break;
         uint32_t r[16];
-        tmem_ld16(tmem + 256 + s * 64 + lane_sel + c, r);
+        tmem_ld16(tmem + TM_D4 + s * 64 + lane_sel + c, r);
         tmem_ld_wait();
         if (rrec.uniform) {
 #pragma unroll
@@ -478,7 +499,7 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
     // =========================================================== M: MMA issuers
     if (lane == 0 && n_my > 0) {
       constexpr uint32_t IDESC1 = idesc_f16(128, 128, 0, 0);   // D1^T[e,j]: A = rbf tile (K-major), B = Wf0 (K-major)
-      constexpr uint32_t IDESC3 = idesc_f16(128, 128, 0, 1);   // D3^T[e,j]: A = gW0 [e][f] (K-major),   B = Wf1 [f][j] (MN-major)
+      constexpr uint32_t IDESC3H = idesc_f16(128, 64, 0, 1);   // D3^T[e,j]: A = gW0 [e][f] (K-major, TMEM), B = Wf1 [f][j] (MN-major)
       constexpr uint32_t IDESC4 = idesc_f16(128, 64, 0, 1);    // D4[e,k]:   A = g_t [e][j] (K-major),   B = Wf0 [j][k] (MN-major)
       const uint64_t dW0k = smem_desc_sw128(sbase + BO_WF0, 16, 1024);          // Wf0 as K-major operand (rows j)
       const uint64_t dW1mn = smem_desc_sw128(sbase + BO_WF1, 128 * 128, 1024);  // Wf1 [f][j] read MN-major (N = j)
@@ -505,13 +526,19 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
         mbar_wait_guard(bar(C_D1_EMPTY + s), ph);  // A(i) has drained D1 from D13[s]
         TR(7, i, 1, true);
         fence_after_sync();
-        const uint64_t dA3 = smem_desc_sw128(sbase + BO_OP + s * (2 * 128 * 128), 16, 1024);   // gW0 [e][f], K-major
+        // A = gW0 [e][f] in tensor memory (8 columns per K = 16 step); two N = 64 halves (filter columns 0-63, 64-127)
 #pragma unroll
         for (int k = 0; k < NF / 16; ++k)
-          mma_f16(tmem + s * 128, dA3 + (uint64_t)((k >> 2) * (128 * 128 / 16) + (k & 3) * 2),
-                  dW1mn + (uint64_t)(k * (2048 / 16)), IDESC3, k > 0);
-        mma_commit(bar(C_OP_EMPTY + s));
+          mma_f16_ts(tmem + s * 128, tmem + TM_GW + s * 64 + k * 8, dW1mn + (uint64_t)(k * (2048 / 16)), IDESC3H, k > 0);
         mma_commit(bar(C_D3_FULL + s));
+        mbar_wait_guard(bar(C_D1E_HI + s), ph);    // A(i) has drained the second half of D1
+        fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < NF / 16; ++k)
+          mma_f16_ts(tmem + s * 128 + 64, tmem + TM_GW + s * 64 + k * 8,
+                     dW1mn + (uint64_t)(128 * 128 / 16 + k * (2048 / 16)), IDESC3H, k > 0);
+        mma_commit(bar(C_OP_EMPTY + s));
+        mma_commit(bar(C_D3F_HI + s));
       };
       auto issue4 = [&](int i) {
         const int s = i & 1;
@@ -525,7 +552,7 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
         const uint64_t dA4 = smem_desc_sw128(sbase + BO_ST + s * (2 * 128 * 128), 16, 1024);   // g_t [e][j], K-major
 #pragma unroll
         for (int k = 0; k < NF / 16; ++k)
-          mma_f16(tmem + 256 + q4 * 64, dA4 + (uint64_t)((k >> 2) * (128 * 128 / 16) + (k & 3) * 2),
+          mma_f16(tmem + TM_D4 + q4 * 64, dA4 + (uint64_t)((k >> 2) * (128 * 128 / 16) + (k & 3) * 2),
                   dB4 + (uint64_t)(k * (2048 / 16)), IDESC4, k > 0);
         mma_commit(bar(C_ST_EMPTY + s));
         mma_commit(bar(C_D4_FULL + q4));

@@ -44,3 +44,7 @@ def print_timeline(trace, names):
         a = np.mean([tr[r, i, 1] - tr[r, i, 0] for i in rows]); b = np.mean([tr[r, i, 2] - tr[r, i, 1] for i in rows])
         line.append(f"{nm} {a:5.0f}/{b:5.0f}")
     print(f"tile period {np.mean(np.diff(tr[0, 8:40, 2])):6.0f} cycles | wait/work per role: " + "  ".join(line))
+    t0 = tr[0, 10, 0]
+    for i in range(10, 15):
+        print(f" tile {i}: " + "  ".join(f"{nm}:{tr[r, i, 0] - t0}/{tr[r, i, 1] - t0}/{tr[r, i, 2] - t0}"
+                                        for r, nm in enumerate(names) if nm != "-" and tr[r, i, 0] > 0))

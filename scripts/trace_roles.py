@@ -17,4 +17,4 @@ for exact in (1, 0):
           "backward %.4f ms per call" % time_ms(bwd))
 trace = torch.zeros(9 * 64 * 3, dtype=torch.int64, device="cuda")
 L.call("fmd_debug_set_trace_bwd", L.ptr(trace)); bwd(); torch.cuda.synchronize(); L.call("fmd_debug_set_trace_bwd", None)
-print_timeline(trace, ["P", "E4", "G", "-", "A", "B", "M1", "M3", "M4"])
+print_timeline(trace, ["P", "E4", "G", "Gmid", "A", "B", "M1", "M3", "M4"])
