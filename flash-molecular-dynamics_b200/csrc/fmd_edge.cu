@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256)
 edge_grad_to_forces_csr_kernel(const float* __restrict__ pos, const int32_t* __restrict__ seg_ptr,
                                const int32_t* __restrict__ dst, const int32_t* __restrict__ rev,
                                const float* __restrict__ dist, const float* __restrict__ g_d, int n_nodes, int n_edges,
-                               float sign, float* __restrict__ out, int accumulate) {
+                               float sign, float* __restrict__ out, int accumulate, int pair_mode) {
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -127,8 +127,13 @@ edge_grad_to_forces_csr_kernel(const float* __restrict__ pos, const int32_t* __r
     for (int e = a + lane; e < b; e += 32) {
       const int j = dst[e];
       const int r = rev[e];
-      float g = g_d[e];
-      if (r >= 0) g += g_d[r];
+      float g;
+      if (pair_mode) {            // rev = pair index of the edge, g_d = the pair's (already symmetrised) gradient
+        g = r >= 0 ? g_d[r] : 0.f;
+      } else {
+        g = g_d[e];
+        if (r >= 0) g += g_d[r];
+      }
       g *= 1.0f / fmaxf(dist[e], 1e-8f);
       fx += g * (pos[3 * j + 0] - px);
       fy += g * (pos[3 * j + 1] - py);
@@ -494,12 +499,13 @@ extern "C" int fmd_edge_grad_to_pos_atomic(const float* pos, const void* edge_sr
 
 extern "C" int fmd_edge_grad_to_forces_csr(const float* pos, const int32_t* seg_ptr, const int32_t* edge_dst,
                                            const int32_t* rev, const float* dist, const float* g_d, int n_nodes,
-                                           int n_edges, float sign, float* out, int accumulate, void* stream) {
+                                           int n_edges, float sign, float* out, int accumulate, int pair_mode,
+                                           void* stream) {
   FMD_REQUIRE(pos && seg_ptr && edge_dst && rev && dist && g_d && out, "fmd_edge_grad_to_forces_csr: bad arguments");
   if (n_nodes == 0) return FMD_OK;
   const int grid = min(fmd_div_up((long long)n_nodes * 32, 256), fmd_num_sms() * 16);
   edge_grad_to_forces_csr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, seg_ptr, edge_dst, rev, dist, g_d,
-                                                                         n_nodes, n_edges, sign, out, accumulate);
+                                                                         n_nodes, n_edges, sign, out, accumulate, pair_mode);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

@@ -1,6 +1,9 @@
-// Fused backward of one interaction block's edge part on the W16A16 path:
+// Fused backward of one interaction block's edge part on the W16A16 path, over UNDIRECTED PAIRS p = (own < nbr):
 //
-//   g_d[e] (+)= d/dd_e  sum_f g_m[own_e,f] * W(d_e)[f] * a[nbr_e,f] * C(d_e)
+//   g[p] (+)= d/dd_p  sum_f W(d_p)[f] * C(d_p) * ( g_m[own,f] a[nbr,f] + g_m[nbr,f] a[own,f] )
+//
+// i.e. the sum of the directed-edge gradients g_d[e] + g_d[rev e] of the reference's backward: the filter depends on
+// the distance alone (W(e) == W(rev e)), and the forces only need that sum, so the kernel runs over half the tiles.
 //
 // replaces the edge part of FusedCSRCFConvFunction.backward (kernels/csr_kernels.py:857-912: fused_grad_filter_out,
 // kernels/cfconv_kernels.py:178-337), the backward GEMMs of the fp16 filter network (LinearFP16ToFP16Function /
@@ -10,7 +13,7 @@
 // Per 128-edge tile, a TMEM lane (= one thread) per EDGE everywhere:
 //   D1^T[e,j] = rbf[e,:] . Wf0[j,:] + b_j          (bias through a constant-1 column)      MMA1
 //   t[e,j]    = tanh(D1^T)                           row e of the stash, fp16
-//   gW0[e,f]  = a[nbr_e,f] * g_m[own_e,f]            row e, fp16
+//   gW0[e,f]  = a[nbr,f] g_m[own,f] + g_m[nbr,f] a[own,f]   row e, fp16 (e = pair index in the tile)
 //   D3^T[e,j] = sum_f gW0[e,f] Wf1[f,j]                                                     MMA3
 //   g_t[e,j]  = C(d_e) D3^T (1 - t^2)                in place over t (K-major A operand)
 //   D4[e,k]   = sum_j g_t[e,j] Wf0[j,k]                                                     MMA4
@@ -20,11 +23,12 @@
 // One persistent CTA per SM, 23 warps (every SIMT role is one serial dependency chain per tile, so the roles - not the
 // issue slots - bound the tile period: five groups of four warps instead of four):
 //   P  warps 0-3    metadata + radial-basis row
-//   G  warps 4-7    rows a[nbr_e,:] (fp16, 256 B) are staged one tile ahead with cp.async (two full rows per instruction,
-//                   coalesced; each warp stages and later reads only ITS 32 rows: cp.async groups, no barrier); thread e
-//                   reads ITS row with 16-byte shared-memory loads, multiplies by g_m[own_e,:] with packed HMUL2 (the g_m
-//                   row is a broadcast 16-byte global load) and writes the fp16 row with tcgen05.st into TENSOR MEMORY,
-//                   where MMA3 reads it as its A operand.  (The kernel is bound by the shared-memory / L1TEX pipe - ncu:
+//   G  warps 4-7    the rows a[nbr,:] and g_m[nbr,:] (fp16, 256 B each) are staged with cp.async through a ring of four
+//                   32-feature slots, one tile ahead, slot by slot into what the warp has just consumed (each warp stages
+//                   and reads only ITS 32 rows: cp.async groups, no barrier); thread e reads ITS row with 16-byte
+//                   shared-memory loads, combines it with the rows of its owner (broadcast 16-byte global loads) with
+//                   packed HMUL2 / HFMA2 and writes the fp16 row with tcgen05.st into TENSOR MEMORY, where MMA3 reads it
+//                   as its A operand.  (The kernel is bound by the shared-memory / L1TEX pipe - ncu:
 //                   77 % of peak with the operand multiplied in place in shared memory and read from there by the MMA;
 //                   per-lane row loads straight from global cost as much in L1TEX: 32 sectors per instruction.)
 //   A  warps 8-11   D1^T -> tanh -> t row (stash)
@@ -50,9 +54,8 @@ constexpr uint32_t TM_D4 = 256, TM_GW = 384;   // tensor-memory column bases
 constexpr uint32_t BO_WF0 = 0;
 constexpr uint32_t BO_WF1 = BO_WF0 + 128 * 128;
 constexpr uint32_t BO_RBF = BO_WF1 + 2 * 128 * 128;          // 2 x 16 KB
-constexpr int APITCH = 272;                                   // bytes per staged row: 256 + 16 (conflict-free 16-byte row-per-lane reads)
-constexpr uint32_t BO_AS = BO_RBF + 2 * 128 * 128;           // 2 x 34 KB: staged rows a[nbr_e,:]
-constexpr uint32_t BO_ST = BO_AS + 2 * TILE * APITCH;        // 2 x 32 KB: t stash, overwritten in place by g_t (A operand of MMA4)
+constexpr uint32_t BO_AS = BO_RBF + 2 * 128 * 128;           // 4 x 16 KB ring: slot q = 32 features of a[nbr] | g_m[nbr], [row][128 B] swizzled
+constexpr uint32_t BO_ST = BO_AS + 4 * TILE * 128;           // 2 x 32 KB: t stash, overwritten in place by g_t (A operand of MMA4)
 constexpr uint32_t BO_META = BO_ST + 2 * 2 * 128 * 128;      // 4 x 1 KB: {byte offset nbr * 256, C(d_e)}
 constexpr uint32_t BO_OWN = BO_META + META_STAGES * TILE * 8;  // 4 x 512 B
 constexpr uint32_t BO_RED = BO_OWN + META_STAGES * TILE * 4;   // 4 x [128] floats: cut-off term sum per edge
@@ -259,54 +262,69 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
       TR(0, i, 2, tid == 0);
     }
   } else if (warp < 8) {
-    // =========================================================== G: gW0 rows (thread = edge row e of the tile)
+    // =========================================================== G: gW0 rows (thread = pair row e of the tile)
     const int w = warp & 3;
     const int e = w * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(w * 32) << 16;
-    const int sub = lane >> 4, ch = lane & 15;                   // copy instruction: two rows x sixteen 16-byte chunks
-    const uint8_t* asrc = reinterpret_cast<const uint8_t*>(a) + ch * 16;
-    auto issue_rows = [&](int i) {
+    const uint32_t e7 = (uint32_t)(e & 7);
+    // copy instruction: 4 rows x {a | g_m} x four 16-byte chunks (64 + 64 bytes per row and slot)
+    const int crow = lane >> 3, cseg = (lane >> 2) & 1, cch = lane & 3;
+    const uint8_t* csrc = reinterpret_cast<const uint8_t*>(cseg ? g_m : a) + cch * 16;
+    auto issue_slot = [&](int i, int q) {
       const int ms = i & (META_STAGES - 1);
-      const uint2* sMeta = reinterpret_cast<const uint2*>(smem + BO_META + ms * TILE * 8) + w * 32 + sub;
-      const uint32_t dst = sbase + BO_AS + (uint32_t)((i & 1) * (TILE * APITCH) + (w * 32 + sub) * APITCH + ch * 16);
+      const uint2* sMeta = reinterpret_cast<const uint2*>(smem + BO_META + ms * TILE * 8) + w * 32 + crow;
+      const uint32_t slot = sbase + BO_AS + (uint32_t)(q * (TILE * 128));
+      // all row offsets first: the copies are `asm volatile` (ordered), a shared-memory load between two of them would
+      // put its latency into every copy
+      uint32_t off[8];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) cp_async16(dst + (uint32_t)(2 * q * APITCH), asrc + sMeta[2 * q].x);
+      for (int k = 0; k < 8; ++k) off[k] = sMeta[4 * k].x;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int row = w * 32 + 4 * k + crow;
+        cp_async16(slot + (uint32_t)(row * 128) + ((((uint32_t)(cseg * 4 + cch)) ^ ((uint32_t)row & 7u)) << 4),
+                   csrc + off[k] + q * 64);
+      }
     };
     if (n_my > 0) {
       mbar_wait_guard(bar(C_META_FULL + 0), 0);
-      issue_rows(0);
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        issue_slot(0, q);
+        cp_async_commit();
+      }
     }
-    cp_async_commit();
     for (int i = 0; i < n_my; ++i) {
       const int s = i & 1, ms = i & (META_STAGES - 1);
+      const bool has_next = i + 1 < n_my;
       TR(2, i, 0, e == 0);
-      // next tile's rows first: their staging buffer was read by this warp one iteration ago (nothing else touches it)
-      if (i + 1 < n_my) {
-        mbar_wait_guard(bar(C_META_FULL + ((i + 1) & (META_STAGES - 1))), ((i + 1) / META_STAGES) & 1);
-        issue_rows(i + 1);
-      }
-      cp_async_commit();
+      if (has_next) mbar_wait_guard(bar(C_META_FULL + ((i + 1) & (META_STAGES - 1))), ((i + 1) / META_STAGES) & 1);
       if (i >= 2) mbar_wait_guard(bar(C_OP_EMPTY + s), ((i - 2) >> 1) & 1);   // MMA3(i-2) has read gW0[s] (tensor memory)
       fence_after_sync();
-      cp_async_wait<1>();          // the rows of tile i have landed ...
-      __syncwarp();                // ... for every lane of this warp
       TR(2, i, 1, e == 0);
       const int own = reinterpret_cast<const int*>(smem + BO_OWN + ms * TILE * 4)[e];
-      const uint4* gmrow = reinterpret_cast<const uint4*>(g_m + (size_t)own * NF);
-      const uint4* arow = reinterpret_cast<const uint4*>(smem + BO_AS + s * (TILE * APITCH) + e * APITCH);
-#pragma unroll
+      const uint4* gm_own = reinterpret_cast<const uint4*>(g_m + (size_t)own * NF);
+      const uint4* a_own = reinterpret_cast<const uint4*>(a + (size_t)own * NF);
+#pragma unroll 1
       for (int q = 0; q < 4; ++q) {
+        cp_async_wait<3>();          // slot q of this tile (committed 4 groups ago) has landed ...
+        __syncwarp();                // ... for every lane of this warp (the rows are private to the warp)
+        const uint8_t* row = smem + BO_AS + q * (TILE * 128) + e * 128;
         uint32_t r[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 av = arow[q * 4 + c];
-          const uint4 gv = __ldg(gmrow + q * 4 + c);
-          r[4 * c + 0] = hmul2_u32(av.x, gv.x);
-          r[4 * c + 1] = hmul2_u32(av.y, gv.y);
-          r[4 * c + 2] = hmul2_u32(av.z, gv.z);
-          r[4 * c + 3] = hmul2_u32(av.w, gv.w);
+          const uint4 aj = *reinterpret_cast<const uint4*>(row + ((((uint32_t)c) ^ e7) << 4));
+          const uint4 gj = *reinterpret_cast<const uint4*>(row + ((((uint32_t)(4 + c)) ^ e7) << 4));
+          const uint4 gi = __ldg(gm_own + q * 4 + c);
+          const uint4 ai = __ldg(a_own + q * 4 + c);
+          r[4 * c + 0] = hfma2_u32(aj.x, gi.x, hmul2_u32(gj.x, ai.x));
+          r[4 * c + 1] = hfma2_u32(aj.y, gi.y, hmul2_u32(gj.y, ai.y));
+          r[4 * c + 2] = hfma2_u32(aj.z, gi.z, hmul2_u32(gj.z, ai.z));
+          r[4 * c + 3] = hfma2_u32(aj.w, gi.w, hmul2_u32(gj.w, ai.w));
         }
         tmem_st16(tmem + TM_GW + s * 64 + lane_sel + q * 16, r);
+        if (has_next) issue_slot(i + 1, q);      // the slot just consumed takes the same features of the next tile
+        cp_async_commit();
       }
       tmem_st_wait();
       fence_before_sync();

@@ -346,8 +346,9 @@ filter_cfconv_fwd_kernel(const float* __restrict__ dist, const int32_t* __restri
     // prefetch of this warp's 64-byte slice of rows [c16*16, c16*16+16) of the tile whose metadata sits in stage `ms`
     auto stage16 = [&](int ms, int c16) {
       const uint32_t* sOff = reinterpret_cast<const uint32_t*>(smem + O_XOFF + ms * TILE * 4) + c16 * 16 + (lane >> 2);
-      cp_async16(xs_dst + (uint32_t)(c16 * 16 * XPITCH), xsrc + sOff[0]);
-      cp_async16(xs_dst + (uint32_t)((c16 * 16 + 8) * XPITCH), xsrc + sOff[8]);
+      const uint32_t o0 = sOff[0], o1 = sOff[8];     // both offsets before the (ordered, asm volatile) copies
+      cp_async16(xs_dst + (uint32_t)(c16 * 16 * XPITCH), xsrc + o0);
+      cp_async16(xs_dst + (uint32_t)((c16 * 16 + 8) * XPITCH), xsrc + o1);
     };
     if (g < n_my) {
       mbar_wait_guard(bar(B_META_FULL + g), 0);

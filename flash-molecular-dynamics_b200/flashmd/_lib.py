@@ -51,7 +51,9 @@ _SIGS = {
     "fmd_edge_grad_to_pos_atomic": ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                      c_void_p, c_void_p], c_int),
     "fmd_edge_grad_to_forces_csr": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                     c_float, c_void_p, c_int, c_void_p], c_int),
+                                     c_float, c_void_p, c_int, c_int, c_void_p], c_int),
+    "fmd_nl_pairs": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "fmd_cfconv_csr": ([c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                         c_int, c_float, c_void_p, c_void_p], c_int),
     "fmd_cfconv_grad_filter": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,

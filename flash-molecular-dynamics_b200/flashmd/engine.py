@@ -343,6 +343,16 @@ class ForceField:
         nb = weights.num_blocks
         if self.fused_tc:
             self.part = torch.zeros(((cap + 127) // 128, F), dtype=f32, device=dev)   # per-tile head partials
+            # undirected pair list (edges with dst > src): the backward edge kernel runs over pairs, half the tiles
+            pcap = self.pair_cap = cap // 2 + 1
+            self.pair_cnt = torch.zeros(N, dtype=i32, device=dev)
+            self.pair_ptr = torch.zeros(N + 1, dtype=i32, device=dev)
+            self.n_pairs_dev = self.pair_ptr[N:]
+            self.pair_own = torch.zeros(pcap, dtype=i32, device=dev)
+            self.pair_nbr = torch.zeros(pcap, dtype=i32, device=dev)
+            self.pair_dist = torch.zeros(pcap, dtype=f32, device=dev)
+            self.pidx = torch.zeros(cap, dtype=i32, device=dev)
+            self.g_pair = torch.zeros(pcap, dtype=f32, device=dev)
         else:
             self.rbf = torch.zeros((cap, R), dtype=f32, device=dev)
             self.t = [torch.zeros((cap, F), dtype=wdt, device=dev) for _ in range(nb)]
@@ -428,11 +438,12 @@ class ForceField:
         self._n += 2
 
     def _filter_cfconv_bwd(self, l, a, g_m):
-        """g_d[e] += d/dd_e of sum_f g_m[src_e,f] W_l(d_e)[f] a[dst_e,f] C(d_e) (fused, tensor cores)."""
+        """g_pair[p] += d/dd_p of sum_f W_l(d_p)[f] C(d_p) (g_m[i,f] a[j,f] + g_m[j,f] a[i,f]) over the undirected pairs
+        p = (i < j): the two directed-edge gradients of the reference's backward in one (fused, tensor cores)."""
         w, k = self.w, self.w.k
-        L.call("fmd_filter_cfconv_bwd", L.ptr(self.dist), L.ptr(self.src), L.ptr(self.dst), self.cap,
-               L.ptr(self.n_edges_dev), L.ptr(k[f"b{l}.f0_w.hp"]), L.ptr(k[f"b{l}.f0_b.h"]), L.ptr(k[f"b{l}.f1_w.h"]),
-               L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(a), L.ptr(g_m), w.filters, L.ptr(self.g_d), 1,
+        L.call("fmd_filter_cfconv_bwd", L.ptr(self.pair_dist), L.ptr(self.pair_own), L.ptr(self.pair_nbr), self.pair_cap,
+               L.ptr(self.n_pairs_dev), L.ptr(k[f"b{l}.f0_w.hp"]), L.ptr(k[f"b{l}.f0_b.h"]), L.ptr(k[f"b{l}.f1_w.h"]),
+               L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(a), L.ptr(g_m), w.filters, L.ptr(self.g_pair), 1,
                int(self.exact), self._st)
         self._n += 1
 
@@ -447,6 +458,11 @@ class ForceField:
         L.call("fmd_nl_reverse", L.ptr(self.seg_ptr), L.ptr(self.src), L.ptr(self.dst), 4, self.N, self.cap,
                L.ptr(self.rev), st)
         self._n += 6
+        if self.fused_tc:
+            L.call("fmd_nl_pairs", L.ptr(self.seg_ptr), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.rev), L.ptr(self.dist),
+                   self.N, self.cap, self.pair_cap, L.ptr(self.pair_cnt), L.ptr(self.pair_ptr), L.ptr(self.scan_ws),
+                   L.ptr(self.pair_own), L.ptr(self.pair_nbr), L.ptr(self.pair_dist), L.ptr(self.pidx), st)
+            self._n += 5
 
     def num_edges(self) -> int:
         """Host read of the live edge count (synchronises)."""
@@ -488,7 +504,7 @@ class ForceField:
         L.call("fmd_segment_sum", L.ptr(self.y[-1]), L.ptr(self.mol_ptr), self.B, L.ptr(self.energy), 0, st)
         self._n += 2
         # ---------------- backward.  [N,K] layout of a backward GEMM's weight == the forward weight's transpose.
-        self.g_d.zero_()
+        self.g_pair.zero_()
         self._n += 1
         gh_cur, gh_nxt = self.g_h[0], self.g_h[1]
         stages = []
@@ -506,8 +522,8 @@ class ForceField:
                 stages = [dict(W=k[f"b{l}.lin1_wT"], res=gh_cur, Y=gh_nxt)]  # g_h <- g_h + g_a @ W1
                 gh_cur, gh_nxt = gh_nxt, gh_cur
                 x = self.g_a
-        L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(self.seg_ptr), L.ptr(self.dst), L.ptr(self.rev),
-               L.ptr(self.dist), L.ptr(self.g_d), self.N, self.cap, 1.0, L.ptr(self.forces), 0, st)
+        L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(self.seg_ptr), L.ptr(self.dst), L.ptr(self.pidx),
+               L.ptr(self.dist), L.ptr(self.g_pair), self.N, self.cap, 1.0, L.ptr(self.forces), 0, 1, st)
         self._n += 1
 
     def _schnet(self, pos):
@@ -573,7 +589,7 @@ class ForceField:
             g = self.g_y[i - 1]
         gh_cur, gh_nxt = self.g_h[0], self.g_h[1]
         self._lin(g, k[f"out0_w{sfx}"], None, gh_cur, x_round=(w16 and g.dtype == torch.float32))
-        self.g_d.zero_()
+        (self.g_pair if tc else self.g_d).zero_()
         self._n += 1
         for l in range(nb - 1, -1, -1):
             # h_{l+1} = h_l + c Wl^T + bl ; c = tanh(m W2^T + b2)
@@ -610,8 +626,12 @@ class ForceField:
             if l > 0:
                 self._lin(self.g_a, k[f"b{l}.lin1_w"], None, gh_nxt, res=gh_cur)
                 gh_cur, gh_nxt = gh_nxt, gh_cur
-        L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(self.seg_ptr), L.ptr(self.dst), L.ptr(self.rev),
-               L.ptr(self.dist), L.ptr(self.g_d), self.N, self.cap, 1.0, L.ptr(self.forces), 0, st)
+        if tc:
+            L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(self.seg_ptr), L.ptr(self.dst), L.ptr(self.pidx),
+                   L.ptr(self.dist), L.ptr(self.g_pair), self.N, self.cap, 1.0, L.ptr(self.forces), 0, 1, st)
+        else:
+            L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(self.seg_ptr), L.ptr(self.dst), L.ptr(self.rev),
+                   L.ptr(self.dist), L.ptr(self.g_d), self.N, self.cap, 1.0, L.ptr(self.forces), 0, 0, st)
         self._n += 1
 
     # -- public ----------------------------------------------------------------------------------

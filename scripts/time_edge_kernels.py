@@ -56,4 +56,4 @@ timeit("dist_rbf_cutoff_fwd", lambda: L.call("fmd_dist_rbf_cutoff_fwd", L.ptr(po
 timeit("rbf_bwd (tiled)", lambda: L.call("fmd_rbf_bwd", L.ptr(ff.dist), L.ptr(grbf), None, E, None, L.ptr(w.centers), R, w.gamma, rc,
        L.ptr(gd), 1, st), 4 * E * R + 12 * E)
 timeit("edge_grad_to_forces_csr", lambda: L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(ff.seg_ptr), L.ptr(ff.dst), L.ptr(ff.rev),
-       L.ptr(ff.dist), L.ptr(gd), N, E, 1.0, L.ptr(ff.forces), 0, st), 16 * E + 24 * N)
+       L.ptr(ff.dist), L.ptr(gd), N, E, 1.0, L.ptr(ff.forces), 0, 0, st), 16 * E + 24 * N)
