@@ -209,8 +209,9 @@ overdamped_kernel(float* __restrict__ pos, const float* __restrict__ forces, con
 
 __global__ void __launch_bounds__(256)
 baoab_post_kernel(float* __restrict__ vel, const float* __restrict__ forces, const float* __restrict__ inv_mass,
-                  int n_nodes, float dt) {
+                  int n_nodes, float dt, uint64_t* __restrict__ step_counter) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && step_counter) *step_counter += 1;      // the step's Philox counter (read by fmd_baoab_pre earlier in the step)
   if (i >= n_nodes) return;
   const float s = 0.5f * dt * inv_mass[i];
 #pragma unroll
@@ -399,12 +400,12 @@ extern "C" int fmd_overdamped_step(float* pos, const float* forces, const float*
 }
 
 extern "C" int fmd_baoab_post(float* vel, const float* forces, const float* inv_mass, int n_nodes, float dt,
-                              const int32_t* mol_ptr, int n_mols, float* ke, void* stream) {
+                              const int32_t* mol_ptr, int n_mols, float* ke, uint64_t* step_counter, void* stream) {
   FMD_REQUIRE(vel && forces && inv_mass, "fmd_baoab_post: bad arguments");
   FMD_REQUIRE(!ke || mol_ptr, "fmd_baoab_post: ke requires mol_ptr");
   if (n_nodes == 0) return FMD_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  baoab_post_kernel<<<fmd_div_up(n_nodes, 256), 256, 0, st>>>(vel, forces, inv_mass, n_nodes, dt);
+  baoab_post_kernel<<<fmd_div_up(n_nodes, 256), 256, 0, st>>>(vel, forces, inv_mass, n_nodes, dt, step_counter);
   if (ke && n_mols > 0) kinetic_kernel<<<n_mols, 256, 0, st>>>(vel, inv_mass, mol_ptr, ke);
   FMD_CHECK_LAUNCH();
   return FMD_OK;

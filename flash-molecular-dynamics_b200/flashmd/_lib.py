@@ -89,7 +89,8 @@ _SIGS = {
     "fmd_overdamped_step": ([c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_uint64, c_int,
                              c_void_p], c_int),
     "fmd_increment_u64": ([c_void_p, c_void_p], c_int),
-    "fmd_baoab_post": ([c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p], c_int),
+    "fmd_baoab_post": ([c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+                       c_int),
     "fmd_philox_normal": ([c_uint64, c_uint64, c_int, c_void_p, c_void_p], c_int),
     "fmd_pt_decide": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_uint64, c_uint64, c_void_p,
                        c_void_p], c_int),

@@ -379,6 +379,8 @@ class ForceField:
         self.g_y = [torch.zeros((N, wd), dtype=odt, device=dev) for wd in widths[:-1]]
         self.ones = torch.ones((N, 1), dtype=odt, device=dev)
         self.launches_per_eval = 0
+        self._embedded = False
+        self._side = None
 
     # -- helpers ---------------------------------------------------------------------------------
     def _lin(self, x, w, bias, y, m_dev=None, **kw):
@@ -437,14 +439,14 @@ class ForceField:
                L.ptr(out), L.ptr(self.part), self._st)
         self._n += 2
 
-    def _filter_cfconv_bwd(self, l, a, g_m):
+    def _filter_cfconv_bwd(self, l, a, g_m, accumulate=True):
         """g_pair[p] += d/dd_p of sum_f W_l(d_p)[f] C(d_p) (g_m[i,f] a[j,f] + g_m[j,f] a[i,f]) over the undirected pairs
         p = (i < j): the two directed-edge gradients of the reference's backward in one (fused, tensor cores)."""
         w, k = self.w, self.w.k
         L.call("fmd_filter_cfconv_bwd", L.ptr(self.pair_dist), L.ptr(self.pair_own), L.ptr(self.pair_nbr), self.pair_cap,
                L.ptr(self.n_pairs_dev), L.ptr(k[f"b{l}.f0_w.hp"]), L.ptr(k[f"b{l}.f0_b.h"]), L.ptr(k[f"b{l}.f1_w.h"]),
-               L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(a), L.ptr(g_m), w.filters, L.ptr(self.g_pair), 1,
-               int(self.exact), self._st)
+               L.ptr(w.centers), w.num_rbf, w.gamma, w.cutoff, L.ptr(a), L.ptr(g_m), w.filters, L.ptr(self.g_pair),
+               int(accumulate), int(self.exact), self._st)
         self._n += 1
 
     # -- neighbour list --------------------------------------------------------------------------
@@ -458,11 +460,28 @@ class ForceField:
         L.call("fmd_nl_reverse", L.ptr(self.seg_ptr), L.ptr(self.src), L.ptr(self.dst), 4, self.N, self.cap,
                L.ptr(self.rev), st)
         self._n += 6
-        if self.fused_tc:
+
+    def _side_work(self, pos):
+        """Work the forward kernels do not depend on, forked onto a second stream right after the neighbour list: the
+        undirected pair list (needed by the backward edge kernel) and ALL prior terms (they depend on positions only and
+        write the force buffer, the SchNet forces are accumulated on top at the end).  In the captured graph this is a
+        parallel branch: the small kernels run in the shadow of the persistent edge kernels."""
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            st = self._side.cuda_stream
             L.call("fmd_nl_pairs", L.ptr(self.seg_ptr), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.rev), L.ptr(self.dist),
                    self.N, self.cap, self.pair_cap, L.ptr(self.pair_cnt), L.ptr(self.pair_ptr), L.ptr(self.scan_ws),
                    L.ptr(self.pair_own), L.ptr(self.pair_nbr), L.ptr(self.pair_dist), L.ptr(self.pidx), st)
             self._n += 5
+            if self.prior_csr is not None:
+                self.prior_csr.launch(pos, self.forces, False, st)
+                self._n += 1
+
+    def _join_side(self):
+        torch.cuda.current_stream().wait_stream(self._side)
 
     def num_edges(self) -> int:
         """Host read of the live edge count (synchronises)."""
@@ -484,10 +503,13 @@ class ForceField:
         nb, no = w.num_blocks, w.num_out_layers
         T, TC = L.ACT_TANH, L.ACT_TANH_CLAMPED
         self.build_neighbor_list(pos)
-        L.call("fmd_embedding", L.ptr(k["embedding"]), L.ptr(self.types), 4, self.N, w.hidden, L.ptr(self.h[0]), st)
-        # a_0 = (Emb W1^T)[types] as fp16 rows (256 B = 64 floats for the row-copy kernel)
-        L.call("fmd_embedding", L.ptr(k["emb_lin1.h"]), L.ptr(self.types), 4, self.N, w.filters // 2, L.ptr(self.a[0]), st)
-        self._n += 2
+        self._side_work(pos)
+        if not self._embedded:
+            # bead types never change during a run: h_0 = Emb[types] and a_0 = (Emb W1^T)[types] are written once
+            # (a_0 as fp16 rows: 256 B = 64 floats for the row-copy kernel)
+            L.call("fmd_embedding", L.ptr(k["embedding"]), L.ptr(self.types), 4, self.N, w.hidden, L.ptr(self.h[0]), st)
+            L.call("fmd_embedding", L.ptr(k["emb_lin1.h"]), L.ptr(self.types), 4, self.N, w.filters // 2, L.ptr(self.a[0]), st)
+            self._embedded = not torch.cuda.is_current_stream_capturing()
         for l in range(nb):
             self._filter_cfconv(l, self.a[l], self.m)
             last = l == nb - 1
@@ -504,8 +526,7 @@ class ForceField:
         L.call("fmd_segment_sum", L.ptr(self.y[-1]), L.ptr(self.mol_ptr), self.B, L.ptr(self.energy), 0, st)
         self._n += 2
         # ---------------- backward.  [N,K] layout of a backward GEMM's weight == the forward weight's transpose.
-        self.g_pair.zero_()
-        self._n += 1
+        self._join_side()      # pair list (+ prior forces in self.forces) from the side stream
         gh_cur, gh_nxt = self.g_h[0], self.g_h[1]
         stages = []
         for i in range(no - 2, 0, -1):      # g_y[i-1] = (g_y[i] @ out_i_w) * (1 - y[i-1]^2), stored as fp16 in the reference
@@ -516,15 +537,20 @@ class ForceField:
             stages.append(dict(W=k[f"b{l}.lin_wT"], aux=self.c[l]))          # g_c = (g_h @ Wl) * (1 - c^2)
             stages.append(dict(W=k[f"b{l}.lin2_wT"], Y=self.g_m))           # g_m = g_c @ W2
             self._chain(x, stages)
-            self._filter_cfconv_bwd(l, self.a[l], self.g_m)
+            self._filter_cfconv_bwd(l, self.a[l], self.g_m, accumulate=(l < nb - 1))   # the first call overwrites g_pair
             if l > 0:   # dE/dh_0 does not enter the forces: no grad_x / g_h update below block 0
                 self._filter_cfconv(l, self.g_m, self.g_a)
                 stages = [dict(W=k[f"b{l}.lin1_wT"], res=gh_cur, Y=gh_nxt)]  # g_h <- g_h + g_a @ W1
                 gh_cur, gh_nxt = gh_nxt, gh_cur
                 x = self.g_a
         L.call("fmd_edge_grad_to_forces_csr", L.ptr(pos), L.ptr(self.seg_ptr), L.ptr(self.dst), L.ptr(self.pidx),
-               L.ptr(self.dist), L.ptr(self.g_pair), self.N, self.cap, 1.0, L.ptr(self.forces), 0, 1, st)
+               L.ptr(self.dist), L.ptr(self.g_pair), self.N, self.cap, 1.0, L.ptr(self.forces),
+               int(self.prior_csr is not None), 1, st)      # on top of the prior forces written by the side stream
         self._n += 1
+        if self.prior_csr is not None:
+            L.call("fmd_segment_sum", L.ptr(self.prior_csr.e_atom), L.ptr(self.mol_ptr), self.B, L.ptr(self.energy), 1, st)
+            self._n += 1
+        self._priors_done = True
 
     def _schnet(self, pos):
         if self._chain_ok():
@@ -534,6 +560,11 @@ class ForceField:
         nb, ned = w.num_blocks, self.n_edges_dev
         self.build_neighbor_list(pos)
         tc = self.fused_tc
+        if tc:
+            L.call("fmd_nl_pairs", L.ptr(self.seg_ptr), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.rev), L.ptr(self.dist),
+                   self.N, self.cap, self.pair_cap, L.ptr(self.pair_cnt), L.ptr(self.pair_ptr), L.ptr(self.scan_ws),
+                   L.ptr(self.pair_own), L.ptr(self.pair_nbr), L.ptr(self.pair_dist), L.ptr(self.pidx), st)
+            self._n += 5
         if not tc:
             # rbf [E,R] (distances were written by the neighbour-list fill)
             L.call("fmd_dist_rbf_cutoff_fwd", L.ptr(pos), L.ptr(self.src), L.ptr(self.dst), 4, self.cap, L.ptr(ned),
@@ -589,14 +620,15 @@ class ForceField:
             g = self.g_y[i - 1]
         gh_cur, gh_nxt = self.g_h[0], self.g_h[1]
         self._lin(g, k[f"out0_w{sfx}"], None, gh_cur, x_round=(w16 and g.dtype == torch.float32))
-        (self.g_pair if tc else self.g_d).zero_()
-        self._n += 1
+        if not tc:
+            self.g_d.zero_()
+            self._n += 1
         for l in range(nb - 1, -1, -1):
             # h_{l+1} = h_l + c Wl^T + bl ; c = tanh(m W2^T + b2)
             self._lin(gh_cur, k[f"b{l}.lin_w"], None, self.g_c, aux=self.c[l])
             self._lin(self.g_c, k[f"b{l}.lin2_w"], None, self.g_m)
             if tc:
-                self._filter_cfconv_bwd(l, self.a[l], self.g_m)
+                self._filter_cfconv_bwd(l, self.a[l], self.g_m, accumulate=(l < nb - 1))
                 if l > 0:      # dE/dh_0 (the embedding gradient) is not needed for forces: skip g_a / g_h of block 0
                     self._filter_cfconv(l, self.g_m, self.g_a)
                     self._lin(self.g_a, k[f"b{l}.lin1_w"], None, gh_nxt, res=gh_cur)
@@ -640,13 +672,14 @@ class ForceField:
         assert pos.is_cuda and pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape == (self.N, 3)
         self._st = L.stream_ptr()
         self._n = 0
+        self._priors_done = False
         if self.w is not None:
             self._schnet(pos)      # writes self.energy (per-molecule SchNet energy) and self.forces
         elif self.prior_csr is None:
             self.energy.zero_()
             self.forces.zero_()
             self._n += 2
-        if self.prior_csr is not None:
+        if self.prior_csr is not None and not self._priors_done:
             # all prior classes in one owner-computes launch, then the per-molecule energy reduction
             self.prior_csr.launch(pos, self.forces, self.w is not None, self._st)
             L.call("fmd_segment_sum", L.ptr(self.prior_csr.e_atom), L.ptr(self.mol_ptr), self.B, L.ptr(self.energy),
@@ -706,11 +739,10 @@ class LangevinEngine:
         L.call("fmd_baoab_pre", L.ptr(self.pos), L.ptr(self.vel), L.ptr(ff.forces), L.ptr(self.inv_mass),
                L.ptr(self.noise_std), L.ptr(noise), self.seed, 0, L.ptr(self.step_dev), self.node_offset, ff.N, self.dt, self.vscale,
                self.noisescale, st)
-        L.call("fmd_increment_u64", L.ptr(self.step_dev), st)
         ff.compute(self.pos)
         L.call("fmd_baoab_post", L.ptr(self.vel), L.ptr(ff.forces), L.ptr(self.inv_mass), ff.N, self.dt,
-               L.ptr(ff.mol_ptr), ff.B, L.ptr(self.ke), st)
-        self.launches_per_step = ff.launches_per_eval + 4
+               L.ptr(ff.mol_ptr), ff.B, L.ptr(self.ke), L.ptr(self.step_dev), st)      # (+ the Philox step counter)
+        self.launches_per_step = ff.launches_per_eval + 3
 
     def step(self, noise: Optional[torch.Tensor] = None):
         """One BAOAB step.  `noise` [N,3] replaces the Philox stream (step-exact parity tests)."""

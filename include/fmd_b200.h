@@ -353,9 +353,10 @@ int fmd_overdamped_step(float* pos, const float* forces, const float* dtau, cons
 int fmd_increment_u64(uint64_t* counter, void* stream);
 
 /* replaces: final B half-kick (simulation/langevin.py:169) (+ optional kinetic energy per molecule:
- * ke[b] = 0.5 sum m v^2, langevin.py:266-270, when ke != NULL; mol_ptr then required). */
+ * ke[b] = 0.5 sum m v^2, langevin.py:266-270, when ke != NULL; mol_ptr then required).
+ * step_counter (nullable): *step_counter += 1, the device-side Philox step counter of a graph-replayed step. */
 int fmd_baoab_post(float* vel, const float* forces, const float* inv_mass, int n_nodes, float dt,
-                   const int32_t* mol_ptr, int n_mols, float* ke, void* stream);
+                   const int32_t* mol_ptr, int n_mols, float* ke, uint64_t* step_counter, void* stream);
 
 /* standard-normal stream used by fmd_baoab_pre when noise == NULL, exposed for tests. out [n_nodes,3]. */
 int fmd_philox_normal(uint64_t seed, uint64_t step, int n_nodes, float* out, void* stream);
