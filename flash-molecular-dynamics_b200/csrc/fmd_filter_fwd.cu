@@ -286,17 +286,17 @@ filter_cfconv_fwd_kernel(const float* __restrict__ dist, const int32_t* __restri
       const int s = i & 1, ms = i & (META_STAGES - 1);
       const uint32_t ph = (i >> 1) & 1;
       TR(1, i, 0, j == 0);
-      mbar_wait_guard(bar(B_D1_FULL + s), ph);
-      mbar_wait_guard(bar(B_TT_EMPTY + s), ph ^ 1);
+      mbar_wait2_guard(bar(B_D1_FULL + s), ph, bar(B_TT_EMPTY + s), ph ^ 1);
       TR(1, i, 1, j == 0);
       fence_after_sync();
       uint8_t* sTT = smem + O_TT + s * (2 * 128 * 128) + jrow;
       const uint4* sCutH = reinterpret_cast<const uint4*>(smem + O_CUT + ms * TILE * 2);   // 8 fp16 cut-offs per load
       const uint32_t d1 = tmem + s * 128 + lane_sel;
-      // t * C(d_e): D2 is linear in t, so the cut-off rides through the second GEMM for free.  tanh on packed fp16 pairs:
-      // one MUFU operation and one HMUL2 per two values (the bias arrived through the GEMM).  The role is bound by the MUFU
-      // pipe (tanh.approx.f16x2 issues every 16 cycles per sub-partition), so the TMEM load of the next 32 columns is in
-      // flight while the current 32 go through it.
+      // t * C(d_e): D2 is linear in t, so the cut-off rides through the second GEMM for free.  tanh.approx.f32 per value,
+      // one F2FP pack and one HMUL2 per two values (the bias arrived through the GEMM; the packed-fp16 tanh is no cheaper:
+      // it is issued as two MUFU operations plus a pack before and a PRMT after).  The MUFU pipe issues one warp
+      // instruction every 8 cycles per sub-partition, so the TMEM load of the next 32 columns is in flight while the
+      // current 32 go through it.
       auto process = [&](const uint32_t (&r)[32], int c) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -305,8 +305,8 @@ filter_cfconv_fwd_kernel(const float* __restrict__ dist, const int32_t* __restri
           uint32_t p[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            p[u] = hmul2_u32(tanh_approx_h2(pack_half2(__uint_as_float(r[q * 8 + 2 * u]), __uint_as_float(r[q * 8 + 2 * u + 1]))),
-                             cc[u]);
+            p[u] = hmul2_u32(pack_half2(tanh_approx(__uint_as_float(r[q * 8 + 2 * u])),
+                                        tanh_approx(__uint_as_float(r[q * 8 + 2 * u + 1]))), cc[u]);
           const int chunk = c * 4 + q;
           *reinterpret_cast<uint4*>(sTT + (chunk >> 3) * (128 * 128) + ((((uint32_t)chunk & 7u) ^ jx) << 4)) =
               make_uint4(p[0], p[1], p[2], p[3]);
@@ -366,8 +366,8 @@ filter_cfconv_fwd_kernel(const float* __restrict__ dist, const int32_t* __restri
       const int* sOwn = reinterpret_cast<const int*>(smem + O_OWN + ms * TILE * 4);
       const uint32_t* sMask = reinterpret_cast<const uint32_t*>(smem + O_HEAD + ms * 32 + 16);
       TR(2 + g, i, 0, f == 0);
-      mbar_wait_guard(bar(B_META_FULL + ms), mph);
-      if (has_next) mbar_wait_guard(bar(B_META_FULL + ms2), ((i + 2) / META_STAGES) & 1);
+      if (has_next) mbar_wait2_guard(bar(B_META_FULL + ms), mph, bar(B_META_FULL + ms2), ((i + 2) / META_STAGES) & 1);
+      else mbar_wait_guard(bar(B_META_FULL + ms), mph);
       int cur = sOwn[0];
       bool head = *reinterpret_cast<const int*>(smem + O_HEAD + ms * 32) == cur;  // run began in an earlier tile
       float acc = 0.f;

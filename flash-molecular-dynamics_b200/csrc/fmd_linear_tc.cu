@@ -22,8 +22,8 @@ constexpr int LT_GROUPS = 2;                  // two 128-thread groups per CTA w
 constexpr int LT_THREADS = LT_TILE * LT_GROUPS;
 constexpr uint32_t LO_A = 0;                  // per group: up to 4 K-blocks x [128 rows][128 B] = 64 KB
 constexpr uint32_t LO_B = 2 * 64 * 1024;      // shared: up to 4 K-blocks x [128 n][128 B]     = 64 KB
-constexpr uint32_t LO_BIAS = 3 * 64 * 1024;   // 128 floats
-constexpr uint32_t LO_BAR = LO_BIAS + 512;
+constexpr uint32_t LO_BIAS = 3 * 64 * 1024;   // 2 x 128 floats (the chain kernel double-buffers the bias row)
+constexpr uint32_t LO_BAR = LO_BIAS + 1024;
 constexpr uint32_t LT_SMEM = LO_BAR + 32;
 constexpr uint32_t LT_SMEM_ALLOC = LT_SMEM + 1024;
 
@@ -45,6 +45,14 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, 
 __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // both tanh flavours map to the hardware tanh.approx.f32 (|err| <= 2^-11, the TF32 operand rounding level of
 // this kernel); the exact tanhf / clamped-exp variants live in the fp32 kernel (fmd_linear.cu)
 __device__ __forceinline__ float act(float v, int a) { return a == FMD_ACT_NONE ? v : tanh_approx(v); }
@@ -283,9 +291,68 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
   const uint64_t dA = smem_desc_sw128(sbase + LO_A + group * (64 * 1024), 16, 1024);
   const uint64_t dB = smem_desc_sw128(sbase + LO_B, 16, 1024);
   uint32_t it = 0;
+  // Stage weights [N][K] -> K-major TF32 B operand in the one shared weight buffer.  fp32 weights are copied with
+  // cp.async (16-byte chunks straight to their swizzled position, no registers held, issued as soon as the previous
+  // stage's MMAs have released the buffer and complete under the epilogue) and rounded to TF32 in place by the thread
+  // that copied them; fp16 weights (the W16A16 output network) go through registers.
+  auto w_issue = [&](const fmd_dense_stage& S, int K, float* bias_dst) {
+    if (S.wdt != FMD_F32) return;
+    const int kc = K >> 2, kc_shift = (K == 128) ? 5 : 4;
+    const int N = S.N, total = N << kc_shift;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = u * CH_THREADS + tid_all;
+      const int n = idx >> kc_shift, c = idx & (kc - 1);
+      if (idx < total)
+        cp_async16(sbase + LO_B + (uint32_t)((c >> 3) * (N * 128)) + sw128_off(n, c & 7),
+                   reinterpret_cast<const float*>(S.W) + (size_t)idx * 4);
+    }
+    if (tid_all < N) {
+      if (S.bias) cp_async4(smem_u32(bias_dst + tid_all), reinterpret_cast<const float*>(S.bias) + tid_all);
+      else bias_dst[tid_all] = 0.f;
+    }
+    cp_async_commit();
+  };
+  auto w_finish = [&](const fmd_dense_stage& S, int K, float* bias_dst) {
+    const int kc = K >> 2, kc_shift = (K == 128) ? 5 : 4;
+    const int N = S.N, total = N << kc_shift;
+    if (S.wdt == FMD_F32) {
+      cp_async_wait_all();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = u * CH_THREADS + tid_all;
+        const int n = idx >> kc_shift, c = idx & (kc - 1);
+        if (idx < total) {
+          float4* slot = reinterpret_cast<float4*>(smem + LO_B + (c >> 3) * (N * 128) + sw128_off(n, c & 7));
+          float4 t = *slot;
+          *slot = make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
+        }
+      }
+      return;
+    }
+    float4 wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = u * CH_THREADS + tid_all;
+      wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < total) wv[u] = load4(reinterpret_cast<const __half*>(S.W) + (size_t)idx * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = u * CH_THREADS + tid_all;
+      const int n = idx >> kc_shift, c = idx & (kc - 1);
+      if (idx < total) *reinterpret_cast<float4*>(smem + LO_B + (c >> 3) * (N * 128) + sw128_off(n, c & 7)) = wv[u];
+    }
+    if (tid_all < N) bias_dst[tid_all] = S.bias ? __half2float(reinterpret_cast<const __half*>(S.bias)[tid_all]) : 0.f;
+  };
   for (int tile0 = blockIdx.x * LT_GROUPS; tile0 < n_tiles; tile0 += gridDim.x * LT_GROUPS) {
     const int m0 = (tile0 + group) * LT_TILE;   // may lie beyond M for the second group: rows are then all invalid
-    // ---- stage pro(X) tile
+    if (it > 0) {          // a previous tile pass: its epilogue is done with sA, its MMAs have released the weight buffer
+      fence_before_sync();
+      __syncthreads();
+    }
+    // ---- weights of stage 0 are in flight while the pro(X) tile is staged
+    w_issue(ca.st[0], K0, sBias);
     {
       const int kc = K0 >> 2, kc_shift = (K0 == 128) ? 5 : 4;
       const int total = LT_TILE << kc_shift;
@@ -314,36 +381,13 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
     for (int s = 0; s < ca.n_stages; ++s) {
       const fmd_dense_stage& S = ca.st[s];
       const int N = S.N;
-      fence_before_sync();
-      __syncthreads();   // both groups are done with the previous stage's weights (their MMAs completed)
-      // ---- stage-s weights [N][K] -> K-major B operand, all 256 threads, 8 chunks in flight
-      {
-        const int kc = K >> 2, kc_shift = (K == 128) ? 5 : 4;
-        const int total = N << kc_shift;
-        for (int base = 0; base < total; base += CH_THREADS * 4) {
-          float4 v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * CH_THREADS + tid_all;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < total) v[u] = load4_dt(S.W, (size_t)idx * 4, S.wdt);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * CH_THREADS + tid_all;
-            const int n = idx >> kc_shift, c = idx & (kc - 1);
-            float4 t = v[u];
-            t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
-            if (idx < total) *reinterpret_cast<float4*>(smem + LO_B + (c >> 3) * (N * 128) + sw128_off(n, c & 7)) = t;
-          }
-        }
-        if (tid_all < N)
-          sBias[tid_all] = S.bias ? (S.wdt == FMD_F16 ? __half2float(reinterpret_cast<const __half*>(S.bias)[tid_all])
-                                                       : reinterpret_cast<const float*>(S.bias)[tid_all])
-                                  : 0.f;
-      }
+      const float* sBiasS = sBias + (s & 1) * 128;
+      const bool feed = s + 1 < ca.n_stages;
+      const bool post = S.aux || S.res || S.Y;
+      w_finish(S, K, sBias + (s & 1) * 128);
       fence_async_smem();
-      __syncthreads();
+      fence_before_sync();
+      __syncthreads();   // operand tiles (A: staging / previous epilogue, B: weights) complete and visible
       if (tid == 0) {
         fence_after_sync();
         const uint32_t idesc = idesc_tf32(128, N, 0, 0);
@@ -353,17 +397,59 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
                    dB + (uint64_t)((k >> 2) * b_kblock + (k & 3) * 2), idesc, k > 0);
         mma_commit(bar);
       }
+      const int nc = N >> 2, nc_shift = (N == 128) ? 5 : 4;
+      const int nb = (LT_TILE << nc_shift) / (CH_GROUP * 2);     // batches of two 16-byte chunks per thread
+      float4 avA[2], rvA[2], avB[2], rvB[2];
+      auto p2_issue = [&](int b, float4 (&av)[2], float4 (&rv)[2]) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int idx = (b * 2 + u) * CH_GROUP + tid;
+          const int r = idx >> nc_shift, c = idx & (nc - 1);
+          const size_t o = (size_t)(m0 + r) * N + c * 4;
+          const bool ok = m0 + r < M;
+          av[u] = (S.aux && ok) ? load4_dt(S.aux, o, S.auxdt) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rv[u] = (S.res && ok) ? load4(S.res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto p2_apply = [&](int b, const float4 (&av)[2], const float4 (&rv)[2]) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int idx = (b * 2 + u) * CH_GROUP + tid;
+          const int r = idx >> nc_shift, c = idx & (nc - 1);
+          float4* slot = reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(r, c & 7));
+          float4 v = *slot;
+          v.x = fmaf(v.x, -av[u].x * av[u].x, v.x) + rv[u].x;     // v * (1 - aux^2) + res
+          v.y = fmaf(v.y, -av[u].y * av[u].y, v.y) + rv[u].y;
+          v.z = fmaf(v.z, -av[u].z * av[u].z, v.z) + rv[u].z;
+          v.w = fmaf(v.w, -av[u].w * av[u].w, v.w) + rv[u].w;
+          if (S.Y && m0 + r < M) {
+            const size_t o = (size_t)(m0 + r) * N + c * 4;
+            if (S.ydt == FMD_F16) store4(reinterpret_cast<__half*>(S.Y) + o, v);
+            else store4(reinterpret_cast<float*>(S.Y) + o, v);
+          }
+          if (feed) {
+            if (S.round_f16) { v.x = round_h(v.x); v.y = round_h(v.y); v.z = round_h(v.z); v.w = round_h(v.w); }
+            *slot = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+          }
+        }
+      };
       mbar_wait(bar, it & 1u);
       ++it;
       fence_after_sync();
+      // This kernel is one pass per CTA, bound by exposed load latencies rather than by throughput: the next stage's
+      // weights and the first aux / residual chunks of this stage's coalesced epilogue phase leave L2 now
+      if (feed) {
+        fence_before_sync();
+        __syncthreads();   // the MMAs of BOTH groups have completed: the weight buffer takes the next stage
+        w_issue(ca.st[s + 1], N, sBias + ((s + 1) & 1) * 128);
+      }
+      if (post) p2_issue(0, avA, rvA);   // in flight during the accumulator drain
       // ---- epilogue of stage s, two phases:
       //  1. thread r drains accumulator row r: + bias, activation -> row r of the A-operand buffer, in place (the MMA
       //     that read the buffer has completed);
       //  2. the group walks the tile in row-major order, consecutive threads on consecutive 16-byte chunks of a row, so
       //     the aux / residual loads and the output stores are fully coalesced (row-per-thread global access made
       //     this epilogue 5x slower than the GEMM itself); the tile is rewritten as the TF32 operand of the next stage.
-      const bool feed = s + 1 < ca.n_stages;
-      const bool post = S.aux || S.res || S.Y;
       const int cw = N / CSL;                      // columns per slice (multiple of 16)
       for (int c0 = cslice * cw; c0 < (cslice + 1) * cw; c0 += 16) {
         uint32_t rr[16];
@@ -373,7 +459,7 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
         for (int q = 0; q < 4; ++q) {
           float v[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(rr[q * 4 + u]) + sBias[c0 + q * 4 + u];
+          for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(rr[q * 4 + u]) + sBiasS[c0 + q * 4 + u];
           if (S.epi_act) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = act(v[u], S.epi_act);
@@ -388,39 +474,12 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
       }
       if (post) {
         asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(CH_GROUP) : "memory");
-        const int nc = N >> 2, nc_shift = (N == 128) ? 5 : 4;
-        const int total = LT_TILE << nc_shift;
-        for (int base = 0; base < total; base += CH_GROUP * 4) {
-          float4 av[4], rv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * CH_GROUP + tid;
-            const int r = idx >> nc_shift, c = idx & (nc - 1);
-            const size_t o = (size_t)(m0 + r) * N + c * 4;
-            const bool ok = m0 + r < M;
-            av[u] = (S.aux && ok) ? load4_dt(S.aux, o, S.auxdt) : make_float4(0.f, 0.f, 0.f, 0.f);
-            rv[u] = (S.res && ok) ? load4(S.res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * CH_GROUP + tid;
-            const int r = idx >> nc_shift, c = idx & (nc - 1);
-            float4* slot = reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(r, c & 7));
-            float4 v = *slot;
-            v.x = fmaf(v.x, -av[u].x * av[u].x, v.x) + rv[u].x;     // v * (1 - aux^2) + res
-            v.y = fmaf(v.y, -av[u].y * av[u].y, v.y) + rv[u].y;
-            v.z = fmaf(v.z, -av[u].z * av[u].z, v.z) + rv[u].z;
-            v.w = fmaf(v.w, -av[u].w * av[u].w, v.w) + rv[u].w;
-            if (S.Y && m0 + r < M) {
-              const size_t o = (size_t)(m0 + r) * N + c * 4;
-              if (S.ydt == FMD_F16) store4(reinterpret_cast<__half*>(S.Y) + o, v);
-              else store4(reinterpret_cast<float*>(S.Y) + o, v);
-            }
-            if (feed) {
-              if (S.round_f16) { v.x = round_h(v.x); v.y = round_h(v.y); v.z = round_h(v.z); v.w = round_h(v.w); }
-              *slot = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-            }
-          }
+        // double-buffered: the loads of batch b + 1 are in flight while batch b is applied
+        for (int b = 0; b < nb; b += 2) {
+          if (b + 1 < nb) p2_issue(b + 1, avB, rvB);
+          p2_apply(b, avA, rvA);
+          if (b + 2 < nb) p2_issue(b + 2, avA, rvA);
+          if (b + 1 < nb) p2_apply(b + 1, avB, rvB);
         }
       }
       K = N;

@@ -53,6 +53,23 @@ __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 
+// Two barriers at once: both phase checks are issued before either result is consumed, so their latencies overlap
+// (a check of an already-completed phase costs the waiting warp's in-order stream ~100 cycles).
+__device__ __forceinline__ void mbar_wait2_guard(uint32_t bar_a, uint32_t parity_a, uint32_t bar_b, uint32_t parity_b) {
+  uint32_t da, db;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "selp.u32 %1, 1, 0, q;\n\t}"
+      : "=r"(da), "=r"(db)
+      : "r"(bar_a), "r"(parity_a), "r"(bar_b), "r"(parity_b)
+      : "memory");
+  if (!da) mbar_wait_guard(bar_a, parity_a);
+  if (!db) mbar_wait_guard(bar_b, parity_b);
+}
+
 // ---- proxies / tcgen05 fences ---------------------------------------------------------------
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
