@@ -397,38 +397,48 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
                    dB + (uint64_t)((k >> 2) * b_kblock + (k & 3) * 2), idesc, k > 0);
         mma_commit(bar);
       }
-      const int nc = N >> 2, nc_shift = (N == 128) ? 5 : 4;
-      const int nb = (LT_TILE << nc_shift) / (CH_GROUP * 2);     // batches of two 16-byte chunks per thread
+      // coalesced epilogue phase: chunk kk of this thread is 16 bytes at row r0 + kk * rows_per_k, column block c; the
+      // row step is a multiple of 8, so both the swizzled shared-memory slot and the global offset advance by constants
+      const int nc_shift = (N == 128) ? 5 : 4;
+      const int rows_per_k = CH_GROUP >> nc_shift;                 // 16 | 32
+      const int nb = LT_TILE / (rows_per_k * 2);                   // batches of two chunks per thread
+      const int r0 = tid >> nc_shift, c4 = tid & ((N >> 2) - 1);
+      uint8_t* const slot0 = sA + (c4 >> 3) * (128 * 128) + sw128_off(r0, c4 & 7);
+      const uint32_t slot_step = (uint32_t)(rows_per_k >> 3) * 1024u;
+      const size_t o0 = (size_t)(m0 + r0) * N + c4 * 4, o_step = (size_t)rows_per_k * N;
+      const int rlim = M - m0 - r0;                                // chunk kk holds a valid row iff kk * rows_per_k < rlim
+      const bool has_aux = S.aux != nullptr, has_res = S.res != nullptr, has_y = S.Y != nullptr;
+      const bool aux_h = S.auxdt == FMD_F16, y_h = S.ydt == FMD_F16, rnd = S.round_f16 != 0;
       float4 avA[2], rvA[2], avB[2], rvB[2];
       auto p2_issue = [&](int b, float4 (&av)[2], float4 (&rv)[2]) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int idx = (b * 2 + u) * CH_GROUP + tid;
-          const int r = idx >> nc_shift, c = idx & (nc - 1);
-          const size_t o = (size_t)(m0 + r) * N + c * 4;
-          const bool ok = m0 + r < M;
-          av[u] = (S.aux && ok) ? load4_dt(S.aux, o, S.auxdt) : make_float4(0.f, 0.f, 0.f, 0.f);
-          rv[u] = (S.res && ok) ? load4(S.res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int kk = b * 2 + u;
+          const size_t o = o0 + (size_t)kk * o_step;
+          const bool ok = kk * rows_per_k < rlim;
+          av[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_aux && ok) av[u] = aux_h ? load4(reinterpret_cast<const __half*>(S.aux) + o) : load4(reinterpret_cast<const float*>(S.aux) + o);
+          if (has_res && ok) rv[u] = load4(S.res + o);
         }
       };
       auto p2_apply = [&](int b, const float4 (&av)[2], const float4 (&rv)[2]) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int idx = (b * 2 + u) * CH_GROUP + tid;
-          const int r = idx >> nc_shift, c = idx & (nc - 1);
-          float4* slot = reinterpret_cast<float4*>(sA + (c >> 3) * (128 * 128) + sw128_off(r, c & 7));
+          const int kk = b * 2 + u;
+          float4* slot = reinterpret_cast<float4*>(slot0 + (uint32_t)kk * slot_step);
           float4 v = *slot;
           v.x = fmaf(v.x, -av[u].x * av[u].x, v.x) + rv[u].x;     // v * (1 - aux^2) + res
           v.y = fmaf(v.y, -av[u].y * av[u].y, v.y) + rv[u].y;
           v.z = fmaf(v.z, -av[u].z * av[u].z, v.z) + rv[u].z;
           v.w = fmaf(v.w, -av[u].w * av[u].w, v.w) + rv[u].w;
-          if (S.Y && m0 + r < M) {
-            const size_t o = (size_t)(m0 + r) * N + c * 4;
-            if (S.ydt == FMD_F16) store4(reinterpret_cast<__half*>(S.Y) + o, v);
+          if (has_y && kk * rows_per_k < rlim) {
+            const size_t o = o0 + (size_t)kk * o_step;
+            if (y_h) store4(reinterpret_cast<__half*>(S.Y) + o, v);
             else store4(reinterpret_cast<float*>(S.Y) + o, v);
           }
           if (feed) {
-            if (S.round_f16) { v.x = round_h(v.x); v.y = round_h(v.y); v.z = round_h(v.z); v.w = round_h(v.w); }
+            if (rnd) { v.x = round_h(v.x); v.y = round_h(v.y); v.z = round_h(v.z); v.w = round_h(v.w); }
             *slot = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
           }
         }
@@ -458,8 +468,9 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(rr[q * 4 + u]) + sBiasS[c0 + q * 4 + u];
+          const float4 bq = *reinterpret_cast<const float4*>(sBiasS + c0 + q * 4);
+          v[0] = __uint_as_float(rr[q * 4]) + bq.x; v[1] = __uint_as_float(rr[q * 4 + 1]) + bq.y;
+          v[2] = __uint_as_float(rr[q * 4 + 2]) + bq.z; v[3] = __uint_as_float(rr[q * 4 + 3]) + bq.w;
           if (S.epi_act) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = act(v[u], S.epi_act);
