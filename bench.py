@@ -318,6 +318,9 @@ def main():
     for _ in range(max(args.warmup, 3)):
         eng.step()
     edges_start = ff.num_edges()
+    # state at the start of the timed region: the end-to-end leg below restarts from it, so both legs see the same phase of
+    # the trajectory (the synthetic chains relax and lose edges while they run)
+    pos_t0, vel_t0, frc_t0 = eng.pos.clone(), eng.vel.clone(), ff.forces.clone()
     # the timed region is `repeats` back-to-back blocks of exactly K steps, long enough (--min-seconds) that launch jitter
     # and the barrier do not show in the max-over-ranks time; per-step numbers divide back
     torch.cuda.synchronize()
@@ -366,9 +369,10 @@ def main():
     vh = torch.empty((B * n, 3), dtype=torch.float32).pin_memory()
     fh = torch.empty((B * n, 3), dtype=torch.float32).pin_memory()
     eh = torch.empty(B, dtype=torch.float32).pin_memory()
-    ph.copy_(eng.pos); vh.copy_(eng.vel); fh.copy_(ff.forces)
+    ph.copy_(pos_t0); vh.copy_(vel_t0); fh.copy_(frc_t0)
     for _ in range(3):
         eng.step_host(ph, vh, fh, eh)
+    e2e_edges_start = ff.num_edges()
     barrier()
     ev0.record()
     for _ in range(args.steps):
@@ -381,6 +385,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
+    e2e_edges_end = ff.num_edges()
     h2d = 3 * B * n * 3 * 4
     d2h = 3 * B * n * 3 * 4 + B * 4
 
@@ -396,8 +401,10 @@ def main():
             "dtype": "f16 filter-network operands / tf32 node layers / f32 accumulate" if args.precision == "w16a16" else "f32",
             "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": eng.launches_per_step * args.steps,
+                    "ms_per_step": ms_e2e / args.steps, "steps": args.steps, "edges_start": e2e_edges_start,
+                    "edges_end": e2e_edges_end,
+                    "note": "restarts from the state at the start of the device-timed region (same trajectory phase)"},
+            "gpu_launches": eng.launches_per_step * n_timed,
             "launches_per_step": eng.launches_per_step,
             "edges": edges_now, "edges_start": edges_start, "nodes": B * n,
             "per_rank": per_rank,
@@ -599,6 +606,7 @@ def kernel_roofline(ff, eng, args, E):
 
     import flashmd.engine as E_mod
     reps = 3
+    e_before = ff.num_edges()
     E_mod.L.call = timed_call
     try:
         for _ in range(reps):
@@ -606,6 +614,7 @@ def kernel_roofline(ff, eng, args, E):
         torch.cuda.synchronize()
     finally:
         E_mod.L.call = orig_call
+    E = 0.5 * (e_before + ff.num_edges())      # live edge count of the steps that were timed
     table = {}
     for name, evs in timings.items():
         tot = sum(a.elapsed_time(bb) for a, bb in evs)
@@ -629,6 +638,7 @@ def kernel_roofline(ff, eng, args, E):
             ach = flops / (ms * 1e-3) / 1e12
             return {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
                     "frac": ach / tf_sus, "traffic": traffic.get(kname), "algorithmic_flops_per_launch": flops,
+                    "edges": E,
                     "avg_launch_ms": ms, "launches_per_step": len(timings[cname]) // reps,
                     "peak_source": which + " bf16_tflops_sustained (kernel timed inside a long step); burst " +
                                    f"{tf_burst:.0f}",
