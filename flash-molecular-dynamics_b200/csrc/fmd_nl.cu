@@ -12,11 +12,22 @@ namespace {
 constexpr int NL_WARPS = 8;
 constexpr int NL_TILE = 1024;
 
+// Pair outputs (optional, int32 lists only): the undirected pairs are the edges with dst > src in list order.  The count pass
+// also writes deg_hi[c] = number of such edges of centre c; the fill pass writes pair p = pair_ptr[c] + (rank among them).
+struct NlPairs {
+  int32_t* deg_hi;          // count pass
+  const int32_t* pair_ptr;  // fill pass
+  int32_t* own;
+  int32_t* nbr;
+  float* dist;
+  int capacity;
+};
+
 template <bool FILL, typename IdxT>
 __global__ void __launch_bounds__(NL_WARPS * 32)
 nl_kernel(const float* __restrict__ pos, const int32_t* __restrict__ mol_ptr, float rc2, int max_hits,
           int32_t* __restrict__ deg, const int32_t* __restrict__ seg_ptr, int capacity,
-          IdxT* __restrict__ edge_src, IdxT* __restrict__ edge_dst, float* __restrict__ dist) {
+          IdxT* __restrict__ edge_src, IdxT* __restrict__ edge_dst, float* __restrict__ dist, const NlPairs pr) {
   __shared__ float sx[NL_TILE], sy[NL_TILE], sz[NL_TILE];
   const int b = blockIdx.x;
   const int lo = mol_ptr[b], hi = mol_ptr[b + 1];
@@ -34,8 +45,11 @@ nl_kernel(const float* __restrict__ pos, const int32_t* __restrict__ mol_ptr, fl
   }
   int hits = 0;     // hits incl. self so far (for the max_num_neighbors cap)
   int emitted = 0;  // edges emitted so far
-  int out_base = 0;
+  int emitted_hi = 0;  // ... of them with neighbour index > centre index (the undirected pairs listed under this centre)
+  int out_base = 0, pair_base = 0;
   if (FILL && active) out_base = seg_ptr[c];
+  if (FILL && active && pr.pair_ptr) pair_base = pr.pair_ptr[c];
+  const bool want_pairs = FILL ? pr.pair_ptr != nullptr : pr.deg_hi != nullptr;
   for (int t0 = 0; t0 < n; t0 += NL_TILE) {
     const int tn = min(NL_TILE, n - t0);
     __syncthreads();
@@ -70,12 +84,77 @@ nl_kernel(const float* __restrict__ pos, const int32_t* __restrict__ mol_ptr, fl
           if (dist) dist[o] = sqrtf(d2);
         }
       }
+      if (want_pairs) {
+        const bool hi_edge = emit && (t0 + jl > c_local);
+        const unsigned pmask = __ballot_sync(0xffffffffu, hi_edge);
+        if (FILL && hi_edge) {
+          const int p = pair_base + emitted_hi + __popc(pmask & lt);
+          if (p < pr.capacity) {
+            pr.own[p] = c;
+            pr.nbr[p] = lo + t0 + jl;
+            pr.dist[p] = sqrtf(d2);
+          }
+        }
+        emitted_hi += __popc(pmask);
+      }
       hits += __popc(hmask);
       emitted += __popc(emask);
       if (hits >= max_hits) break;  // warp-uniform
     }
   }
-  if (!FILL && active && lane == 0) deg[c] = emitted;
+  if (!FILL && active && lane == 0) {
+    deg[c] = emitted;
+    if (want_pairs) pr.deg_hi[c] = emitted_hi;
+  }
+}
+
+// two exclusive scans in one launch (CTA b scans array b: degrees -> seg_ptr, pair counts -> pair_ptr), 4096 items per pass;
+// out[n] = total.  n is a few 10^4: one CTA per array is faster than the three-kernel scan (three launches per array).
+__global__ void __launch_bounds__(1024)
+scan2_kernel(const int32_t* __restrict__ in0, int32_t* __restrict__ out0, const int32_t* __restrict__ in1,
+             int32_t* __restrict__ out1, int n) {
+  const int32_t* in = blockIdx.x == 0 ? in0 : in1;
+  int32_t* out = blockIdx.x == 0 ? out0 : out1;
+  if (!in || !out) return;
+  __shared__ int ws[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 4096) {
+    const int i = base + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i + k < n) ? in[i + k] : 0;
+    const int tsum = v[0] + v[1] + v[2] + v[3];
+    int x = tsum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = ws[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      ws[lane] = t;  // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int run = carry + (w > 0 ? ws[w - 1] : 0) + x - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i + k < n) out[i + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry_s;
 }
 
 // ---------------------------------------------------------------- exclusive scan (3 phases)
@@ -166,7 +245,8 @@ __global__ void __launch_bounds__(256) scan_apply(const int32_t* __restrict__ in
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 nl_reverse_kernel(const int32_t* __restrict__ seg_ptr, const IdxT* __restrict__ src, const IdxT* __restrict__ dst,
-                  int n_nodes, int capacity, IdxT* __restrict__ rev) {
+                  int n_nodes, int capacity, IdxT* __restrict__ rev, const int32_t* __restrict__ pair_ptr,
+                  int32_t* __restrict__ pidx) {
   const int E = min(seg_ptr[n_nodes], capacity);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
     const int s = (int)src[e], t = (int)dst[e];
@@ -180,6 +260,17 @@ nl_reverse_kernel(const int32_t* __restrict__ seg_ptr, const IdxT* __restrict__ 
       else { found = mid; break; }
     }
     rev[e] = (IdxT)found;
+    if (pidx) {
+      // the pair is listed under its smaller bead `a`, as edge `f` of a's segment; the pairs of a are the tail of the segment
+      const int a = t > s ? s : t;
+      const int f = t > s ? e : found;
+      int p = -1;
+      if (f >= 0) {
+        const int first_hi = min(seg_ptr[a + 1], E) - (pair_ptr[a + 1] - pair_ptr[a]);
+        p = pair_ptr[a] + (f - first_hi);
+      }
+      pidx[e] = p;
+    }
   }
 }
 
@@ -290,7 +381,7 @@ extern "C" int fmd_nl_count(const float* pos, const int32_t* mol_ptr, int n_mols
   dim3 grid(n_mols, fmd_div_up(max_mol_size, NL_WARPS));
   FMD_REQUIRE(grid.y <= 65535, "fmd_nl_count: molecule too large");
   nl_kernel<false, int32_t><<<grid, NL_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      pos, mol_ptr, rc * rc, max_num_neighbors + 1, deg, nullptr, 0, nullptr, nullptr, nullptr);
+      pos, mol_ptr, rc * rc, max_num_neighbors + 1, deg, nullptr, 0, nullptr, nullptr, nullptr, NlPairs{});
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }
@@ -307,11 +398,11 @@ extern "C" int fmd_nl_fill(const float* pos, const int32_t* mol_ptr, int n_mols,
   if (idx_bytes == 4)
     nl_kernel<true, int32_t><<<grid, NL_WARPS * 32, 0, st>>>(pos, mol_ptr, rc * rc, max_num_neighbors + 1, nullptr,
                                                              seg_ptr, capacity, (int32_t*)edge_src,
-                                                             (int32_t*)edge_dst, dist);
+                                                             (int32_t*)edge_dst, dist, NlPairs{});
   else
     nl_kernel<true, int64_t><<<grid, NL_WARPS * 32, 0, st>>>(pos, mol_ptr, rc * rc, max_num_neighbors + 1, nullptr,
                                                              seg_ptr, capacity, (int64_t*)edge_src,
-                                                             (int64_t*)edge_dst, dist);
+                                                             (int64_t*)edge_dst, dist, NlPairs{});
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }
@@ -325,10 +416,10 @@ extern "C" int fmd_nl_reverse(const int32_t* seg_ptr, const void* edge_src, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (idx_bytes == 4)
     nl_reverse_kernel<int32_t><<<grid, 256, 0, st>>>(seg_ptr, (const int32_t*)edge_src, (const int32_t*)edge_dst,
-                                                     n_nodes, capacity, (int32_t*)rev);
+                                                     n_nodes, capacity, (int32_t*)rev, nullptr, nullptr);
   else
     nl_reverse_kernel<int64_t><<<grid, 256, 0, st>>>(seg_ptr, (const int64_t*)edge_src, (const int64_t*)edge_dst,
-                                                     n_nodes, capacity, (int64_t*)rev);
+                                                     n_nodes, capacity, (int64_t*)rev, nullptr, nullptr);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }
@@ -348,6 +439,43 @@ extern "C" int fmd_nl_pairs(const int32_t* seg_ptr, const int32_t* edge_src, con
     const int grid = min(fmd_div_up(capacity, 256), fmd_num_sms() * 8);
     nl_pair_fill_kernel<<<grid, 256, 0, st>>>(seg_ptr, edge_src, edge_dst, rev, dist, pair_ptr, n_nodes, capacity,
                                               pair_capacity, pair_own, pair_nbr, pair_dist, pidx);
+  }
+  FMD_CHECK_LAUNCH();
+  return FMD_OK;
+}
+
+extern "C" int fmd_nl_step(const float* pos, const int32_t* mol_ptr, int n_mols, int n_nodes, int max_mol_size, float rc,
+                           int max_num_neighbors, int32_t* deg, int32_t* seg_ptr, int capacity, int32_t* edge_src,
+                           int32_t* edge_dst, float* dist, int32_t* rev, int32_t* pair_cnt, int32_t* pair_ptr,
+                           int pair_capacity, int32_t* pair_own, int32_t* pair_nbr, float* pair_dist, int32_t* pidx,
+                           void* stream) {
+  FMD_REQUIRE(pos && mol_ptr && deg && seg_ptr && edge_src && edge_dst && dist && rev, "fmd_nl_step: null argument");
+  const bool pairs = pair_cnt != nullptr;
+  FMD_REQUIRE(!pairs || (pair_ptr && pair_own && pair_nbr && pair_dist && pidx), "fmd_nl_step: incomplete pair outputs");
+  if (n_mols == 0 || n_nodes == 0) return FMD_OK;
+  dim3 grid(n_mols, fmd_div_up(max_mol_size, NL_WARPS));
+  FMD_REQUIRE(grid.y <= 65535, "fmd_nl_step: molecule too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float rc2 = rc * rc;
+  NlPairs pc{};
+  pc.deg_hi = pairs ? pair_cnt : nullptr;
+  nl_kernel<false, int32_t><<<grid, NL_WARPS * 32, 0, st>>>(pos, mol_ptr, rc2, max_num_neighbors + 1, deg, nullptr, 0,
+                                                            nullptr, nullptr, nullptr, pc);
+  scan2_kernel<<<pairs ? 2 : 1, 1024, 0, st>>>(deg, seg_ptr, pair_cnt, pair_ptr, n_nodes);
+  NlPairs pf{};
+  if (pairs) {
+    pf.pair_ptr = pair_ptr;
+    pf.own = pair_own;
+    pf.nbr = pair_nbr;
+    pf.dist = pair_dist;
+    pf.capacity = pair_capacity;
+  }
+  nl_kernel<true, int32_t><<<grid, NL_WARPS * 32, 0, st>>>(pos, mol_ptr, rc2, max_num_neighbors + 1, nullptr, seg_ptr,
+                                                           capacity, edge_src, edge_dst, dist, pf);
+  if (capacity > 0) {
+    const int g = min(fmd_div_up(capacity, 256), fmd_num_sms() * 8);
+    nl_reverse_kernel<int32_t><<<g, 256, 0, st>>>(seg_ptr, edge_src, edge_dst, n_nodes, capacity, rev,
+                                                  pairs ? pair_ptr : nullptr, pairs ? pidx : nullptr);
   }
   FMD_CHECK_LAUNCH();
   return FMD_OK;

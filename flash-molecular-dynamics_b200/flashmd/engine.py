@@ -452,6 +452,14 @@ class ForceField:
     # -- neighbour list --------------------------------------------------------------------------
     def build_neighbor_list(self, pos):
         st, w = self._st, self.w
+        if self.fused_tc:
+            # sorted symmetric edge list + reverse map + undirected pair list in four launches
+            L.call("fmd_nl_step", L.ptr(pos), L.ptr(self.mol_ptr), self.B, self.N, self.max_mol, w.cutoff, self.max_nn,
+                   L.ptr(self.deg), L.ptr(self.seg_ptr), self.cap, L.ptr(self.src), L.ptr(self.dst), L.ptr(self.dist),
+                   L.ptr(self.rev), L.ptr(self.pair_cnt), L.ptr(self.pair_ptr), self.pair_cap, L.ptr(self.pair_own),
+                   L.ptr(self.pair_nbr), L.ptr(self.pair_dist), L.ptr(self.pidx), st)
+            self._n += 4
+            return
         L.call("fmd_nl_count", L.ptr(pos), L.ptr(self.mol_ptr), self.B, self.N, self.max_mol, w.cutoff, self.max_nn,
                L.ptr(self.deg), st)
         L.call("fmd_exclusive_scan_i32", L.ptr(self.deg), L.ptr(self.seg_ptr), self.N, L.ptr(self.scan_ws), st)
@@ -462,26 +470,23 @@ class ForceField:
         self._n += 6
 
     def _side_work(self, pos):
-        """Work the forward kernels do not depend on, forked onto a second stream right after the neighbour list: the
-        undirected pair list (needed by the backward edge kernel) and ALL prior terms (they depend on positions only and
-        write the force buffer, the SchNet forces are accumulated on top at the end).  In the captured graph this is a
-        parallel branch: the small kernels run in the shadow of the persistent edge kernels."""
+        """Work the forward kernels do not depend on, forked onto a second stream: ALL prior terms (they depend on
+        positions only and write the force buffer, the SchNet forces are accumulated on top at the end).  In the captured
+        graph this is a parallel branch: the prior kernel runs in the shadow of the first persistent forward kernel, which
+        leaves issue slots idle (forked before the neighbour list it only slows that one down: measured)."""
+        if self.prior_csr is None:
+            return
         if self._side is None:
             self._side = torch.cuda.Stream()
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
-            st = self._side.cuda_stream
-            L.call("fmd_nl_pairs", L.ptr(self.seg_ptr), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.rev), L.ptr(self.dist),
-                   self.N, self.cap, self.pair_cap, L.ptr(self.pair_cnt), L.ptr(self.pair_ptr), L.ptr(self.scan_ws),
-                   L.ptr(self.pair_own), L.ptr(self.pair_nbr), L.ptr(self.pair_dist), L.ptr(self.pidx), st)
-            self._n += 5
-            if self.prior_csr is not None:
-                self.prior_csr.launch(pos, self.forces, False, st)
-                self._n += 1
+            self.prior_csr.launch(pos, self.forces, False, self._side.cuda_stream)
+            self._n += 1
 
     def _join_side(self):
-        torch.cuda.current_stream().wait_stream(self._side)
+        if self.prior_csr is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
 
     def num_edges(self) -> int:
         """Host read of the live edge count (synchronises)."""
@@ -560,11 +565,6 @@ class ForceField:
         nb, ned = w.num_blocks, self.n_edges_dev
         self.build_neighbor_list(pos)
         tc = self.fused_tc
-        if tc:
-            L.call("fmd_nl_pairs", L.ptr(self.seg_ptr), L.ptr(self.src), L.ptr(self.dst), L.ptr(self.rev), L.ptr(self.dist),
-                   self.N, self.cap, self.pair_cap, L.ptr(self.pair_cnt), L.ptr(self.pair_ptr), L.ptr(self.scan_ws),
-                   L.ptr(self.pair_own), L.ptr(self.pair_nbr), L.ptr(self.pair_dist), L.ptr(self.pidx), st)
-            self._n += 5
         if not tc:
             # rbf [E,R] (distances were written by the neighbour-list fill)
             L.call("fmd_dist_rbf_cutoff_fwd", L.ptr(pos), L.ptr(self.src), L.ptr(self.dst), 4, self.cap, L.ptr(ned),

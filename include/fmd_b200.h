@@ -150,6 +150,17 @@ int fmd_nl_pairs(const int32_t* seg_ptr, const int32_t* edge_src, const int32_t*
                  void* scan_workspace, int32_t* pair_own, int32_t* pair_nbr, float* pair_dist, int32_t* pidx,
                  void* stream);
 
+/* replaces: the per-step call of torch_cluster.radius_graph (neighbor_list/torch_impl.py:216-224) + build_csr_index /
+ * build_src_csr_index (kernels/csr_kernels.py:88, 229) of the fused step, in FOUR launches: count (degrees and, if pair
+ * outputs are given, the number of neighbours with a larger index), one launch that scans both count arrays, fill (edge
+ * list + the undirected pair list of fmd_nl_pairs, written directly), reverse map (+ pidx).  Results identical to
+ * fmd_nl_count / fmd_exclusive_scan_i32 / fmd_nl_fill / fmd_nl_reverse / fmd_nl_pairs (int32 indices).
+ * seg_ptr[n_nodes] / pair_ptr[n_nodes] hold the live edge / pair counts on the device.  pair_cnt == NULL: no pair list. */
+int fmd_nl_step(const float* pos, const int32_t* mol_ptr, int n_mols, int n_nodes, int max_mol_size, float rc,
+                int max_num_neighbors, int32_t* deg, int32_t* seg_ptr, int capacity, int32_t* edge_src,
+                int32_t* edge_dst, float* dist, int32_t* rev, int32_t* pair_cnt, int32_t* pair_ptr, int pair_capacity,
+                int32_t* pair_own, int32_t* pair_nbr, float* pair_dist, int32_t* pidx, void* stream);
+
 /* ---------------------------------------------------------------- fused filter network (x) CFConv (tensor cores) */
 
 /* replaces, for the W16A16 path, the chain  GPTQW16A16FilterNetwork.forward (models/gptq.py:92-130:
