@@ -608,12 +608,14 @@ def kernel_roofline(ff, eng, args, E):
     reps = 3
     e_before = ff.num_edges()
     E_mod.L.call = timed_call
+    ff.serial_priors = True      # every kernel alone on the stream: the forked prior kernel would overlap the first forward launch
     try:
         for _ in range(reps):
             eng._step_body()
         torch.cuda.synchronize()
     finally:
         E_mod.L.call = orig_call
+        ff.serial_priors = False
     E = 0.5 * (e_before + ff.num_edges())      # live edge count of the steps that were timed
     table = {}
     for name, evs in timings.items():
@@ -631,7 +633,8 @@ def kernel_roofline(ff, eng, args, E):
             traffic = json.load(open(tp))
         except Exception:
             traffic = {}
-    how = "CUDA events around each launch of an eager (non-graph) step, same stream, averaged over 3 steps"
+    how = ("CUDA events around each launch of an eager (non-graph) step, every kernel alone on the stream (the prior kernel, "
+           "forked in the real step, runs serially here), averaged over 3 steps")
     if "fmd_filter_cfconv_fwd" in timings:
         def tensor_roof(cname, kname, flops):
             ms = avg_ms(cname)

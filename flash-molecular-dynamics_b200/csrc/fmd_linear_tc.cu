@@ -254,6 +254,7 @@ __device__ __forceinline__ float round_h(float v) { return __half2float(__float2
 constexpr int CH_GROUP = 512;
 constexpr int CH_THREADS = CH_GROUP * LT_GROUPS;
 
+template <int tpc>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int pro_act, int x_round_f16,
                        const __grid_constant__ ChainArgs ca) {
@@ -345,15 +346,19 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
     }
     if (tid_all < N) bias_dst[tid_all] = S.bias ? __half2float(reinterpret_cast<const __half*>(S.bias)[tid_all]) : 0.f;
   };
-  for (int tile0 = blockIdx.x * LT_GROUPS; tile0 < n_tiles; tile0 += gridDim.x * LT_GROUPS) {
+  // tpc = row tiles per CTA and pass: 2 (both groups busy) when there are more tiles than SMs, else 1 - the second group
+  // then only helps to stage the weights, and twice as many SMs work (small systems: 54 beads x 128 molecules = 54 tiles)
+  const bool live = group < tpc;
+  int pass = 0;
+  for (int tile0 = blockIdx.x * tpc; tile0 < n_tiles; tile0 += gridDim.x * tpc, ++pass) {
     const int m0 = (tile0 + group) * LT_TILE;   // may lie beyond M for the second group: rows are then all invalid
-    if (it > 0) {          // a previous tile pass: its epilogue is done with sA, its MMAs have released the weight buffer
+    if (pass > 0) {        // a previous tile pass: its epilogue is done with sA, its MMAs have released the weight buffer
       fence_before_sync();
       __syncthreads();
     }
     // ---- weights of stage 0 are in flight while the pro(X) tile is staged
     w_issue(ca.st[0], K0, sBias);
-    {
+    if (live) {
       const int kc = K0 >> 2, kc_shift = (K0 == 128) ? 5 : 4;
       const int total = LT_TILE << kc_shift;
       for (int base = 0; base < total; base += CH_GROUP * 4) {
@@ -388,7 +393,7 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
       fence_async_smem();
       fence_before_sync();
       __syncthreads();   // operand tiles (A: staging / previous epilogue, B: weights) complete and visible
-      if (tid == 0) {
+      if (tid == 0 && live) {
         fence_after_sync();
         const uint32_t idesc = idesc_tf32(128, N, 0, 0);
         const uint32_t b_kblock = (uint32_t)(N * 128 / 16);
@@ -443,8 +448,10 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
           }
         }
       };
-      mbar_wait(bar, it & 1u);
-      ++it;
+      if (live) {
+        mbar_wait(bar, it & 1u);
+        ++it;
+      }
       fence_after_sync();
       // This kernel is one pass per CTA, bound by exposed load latencies rather than by throughput: the next stage's
       // weights and the first aux / residual chunks of this stage's coalesced epilogue phase leave L2 now
@@ -452,6 +459,10 @@ linear_chain_tc_kernel(const void* __restrict__ X, int xdt, int M, int K0, int p
         fence_before_sync();
         __syncthreads();   // the MMAs of BOTH groups have completed: the weight buffer takes the next stage
         w_issue(ca.st[s + 1], N, sBias + ((s + 1) & 1) * 128);
+      }
+      if (!live) {
+        K = N;
+        continue;
       }
       if (post) p2_issue(0, avA, rvA);   // in flight during the accumulator drain
       // ---- epilogue of stage s, two phases:
@@ -563,12 +574,18 @@ extern "C" int fmd_linear_chain_tc(const void* X, int xdt, int M, int K, int pro
   if (M == 0) return FMD_OK;
   static bool attr_done = false;
   if (!attr_done) {
-    FMD_CUDA(cudaFuncSetAttribute(linear_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM_ALLOC));
+    FMD_CUDA(cudaFuncSetAttribute(linear_chain_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM_ALLOC));
+    FMD_CUDA(cudaFuncSetAttribute(linear_chain_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM_ALLOC));
     attr_done = true;
   }
-  const int pairs = fmd_div_up(fmd_div_up(M, LT_TILE), LT_GROUPS);
-  const int grid = pairs < fmd_num_sms() ? pairs : fmd_num_sms();
-  linear_chain_tc_kernel<<<grid, CH_THREADS, LT_SMEM_ALLOC, (cudaStream_t)stream>>>(X, xdt, M, K, pro_act, x_round_f16, ca);
+  const int n_tiles = fmd_div_up(M, LT_TILE);
+  const int tpc = n_tiles <= fmd_num_sms() ? 1 : LT_GROUPS;
+  const int want = fmd_div_up(n_tiles, tpc);
+  const int grid = want < fmd_num_sms() ? want : fmd_num_sms();
+  if (tpc == 1)
+    linear_chain_tc_kernel<1><<<grid, CH_THREADS, LT_SMEM_ALLOC, (cudaStream_t)stream>>>(X, xdt, M, K, pro_act, x_round_f16, ca);
+  else
+    linear_chain_tc_kernel<2><<<grid, CH_THREADS, LT_SMEM_ALLOC, (cudaStream_t)stream>>>(X, xdt, M, K, pro_act, x_round_f16, ca);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

@@ -381,6 +381,7 @@ class ForceField:
         self.launches_per_eval = 0
         self._embedded = False
         self._side = None
+        self.serial_priors = False     # True: prior kernel on the main stream instead of the forked one (per-kernel timing)
 
     # -- helpers ---------------------------------------------------------------------------------
     def _lin(self, x, w, bias, y, m_dev=None, **kw):
@@ -476,6 +477,10 @@ class ForceField:
         leaves issue slots idle (forked before the neighbour list it only slows that one down: measured)."""
         if self.prior_csr is None:
             return
+        if self.serial_priors:          # per-kernel timing (bench.py): nothing overlaps, every kernel is timed alone
+            self.prior_csr.launch(pos, self.forces, False, self._st)
+            self._n += 1
+            return
         if self._side is None:
             self._side = torch.cuda.Stream()
         main = torch.cuda.current_stream()
@@ -485,7 +490,7 @@ class ForceField:
             self._n += 1
 
     def _join_side(self):
-        if self.prior_csr is not None:
+        if self.prior_csr is not None and not self.serial_priors:
             torch.cuda.current_stream().wait_stream(self._side)
 
     def num_edges(self) -> int:

@@ -84,6 +84,53 @@ def test_radius_graph_csr_bit_exact(case, idx_dtype):
         np.testing.assert_array_equal(rev, perm)
 
 
+@pytest.mark.parametrize("case", [
+    dict(seed=0, sizes=[54] * 4, box=14.0, rc=6.0),
+    dict(seed=1, sizes=[1, 2, 33, 7, 130, 64], box=10.0, rc=3.5),
+    dict(seed=2, sizes=[1200, 17], box=30.0, rc=5.0),
+    dict(seed=3, sizes=[40, 40], box=3.0, rc=50.0),
+    dict(seed=5, sizes=[5, 5], box=100.0, rc=0.01),
+])
+def test_fused_step_neighbor_and_pair_list_bit_exact(case):
+    """fmd_nl_step (the four-launch neighbour list of the fused step): edge list, CSR, reverse map == oracle; the
+    undirected pair list == the edges with dst > src in list order; pidx maps both directions of a pair to it."""
+    from flashmd import _lib as L
+    pos, ptr = _random_molecules(case["seed"], case["sizes"], case["box"])
+    ref = O.radius_graph(pos, ptr, case["rc"], 1000)
+    N, E = pos.shape[0], ref.shape[1]
+    cap, pcap = E + 64, E // 2 + 8
+    i32 = dict(dtype=torch.int32, device=DEV)
+    posd = torch.from_numpy(pos).to(DEV).contiguous()
+    mol_ptr = torch.from_numpy(ptr.astype(np.int32)).to(DEV)
+    deg, seg = torch.zeros(N, **i32), torch.zeros(N + 1, **i32)
+    src, dst, rev, pidx = (torch.full((cap,), -7, **i32) for _ in range(4))
+    dist = torch.zeros(cap, device=DEV)
+    pcnt, pptr = torch.zeros(N, **i32), torch.zeros(N + 1, **i32)
+    pown, pnbr = torch.full((pcap,), -7, **i32), torch.full((pcap,), -7, **i32)
+    pdist = torch.zeros(pcap, device=DEV)
+    L.call("fmd_nl_step", L.ptr(posd), L.ptr(mol_ptr), len(case["sizes"]), N, max(case["sizes"]), case["rc"], 1000,
+           L.ptr(deg), L.ptr(seg), cap, L.ptr(src), L.ptr(dst), L.ptr(dist), L.ptr(rev), L.ptr(pcnt), L.ptr(pptr), pcap,
+           L.ptr(pown), L.ptr(pnbr), L.ptr(pdist), L.ptr(pidx), L.stream_ptr())
+    torch.cuda.synchronize()
+    assert int(seg[N]) == E
+    np.testing.assert_array_equal(torch.stack([src[:E], dst[:E]]).cpu().numpy().astype(np.int64), ref)
+    sptr, _ = O.build_csr(ref[0], N)
+    np.testing.assert_array_equal(seg.cpu().numpy().astype(np.int64), sptr)
+    np.testing.assert_array_equal(rev[:E].cpu().numpy().astype(np.int64), O.reverse_edge_index(ref, N))
+    hi = ref[1] > ref[0]
+    P = int(hi.sum())
+    assert int(pptr[N]) == P == E // 2
+    np.testing.assert_array_equal(pown[:P].cpu().numpy(), ref[0][hi])
+    np.testing.assert_array_equal(pnbr[:P].cpu().numpy(), ref[1][hi])
+    np.testing.assert_array_equal(pdist[:P].cpu().numpy(), dist[:E].cpu().numpy()[hi])
+    pi = pidx[:E].cpu().numpy()
+    np.testing.assert_array_equal(pi[hi], np.arange(P))                               # forward direction: list order
+    lo_own, lo_nbr = ref[0][~hi], ref[1][~hi]                                         # reverse direction: same pair
+    np.testing.assert_array_equal(pown[:P].cpu().numpy()[pi[~hi]], lo_nbr)
+    np.testing.assert_array_equal(pnbr[:P].cpu().numpy()[pi[~hi]], lo_own)
+    assert (src[E:] == -7).all() and (pown[P:] == -7).all()                           # nothing written beyond the live counts
+
+
 @pytest.mark.parametrize("name", ["schnet_n54_b4.npz", "schnet_n24_b3_l2.npz", "schnet_n40_b2_l5.npz"])
 def test_radius_graph_golden(name):
     g = load_golden(name)
