@@ -889,16 +889,50 @@ def random_schnet_tensors(seed: int, num_rbf: int = 50, hidden: int = 128, filte
 
 def _step_host(self, pos_h, vel_h, forces_h, energy_h):
     """End-to-end step with HOST state: pinned pos/vel/forces -> device, one BAOAB step, new
-    pos/vel/forces + per-molecule potential back to the pinned host buffers (synchronises)."""
-    self.pos.copy_(pos_h, non_blocking=True)
-    self.vel.copy_(vel_h, non_blocking=True)
-    self.ff.forces.copy_(forces_h, non_blocking=True)
-    self.step()
-    pos_h.copy_(self.pos, non_blocking=True)
-    vel_h.copy_(self.vel, non_blocking=True)
-    forces_h.copy_(self.ff.forces, non_blocking=True)
-    energy_h.copy_(self.ff.energy, non_blocking=True)
+    pos/vel/forces + per-molecule potential back to the pinned host buffers (synchronises).
+
+    With pinned buffers the copies are part of the captured graph (one graph per set of host buffers): one launch and one
+    synchronisation per step instead of seven copy calls around the step graph."""
+    bufs = (pos_h, vel_h, forces_h, energy_h)
+
+    def body():
+        self.pos.copy_(pos_h, non_blocking=True)
+        self.vel.copy_(vel_h, non_blocking=True)
+        self.ff.forces.copy_(forces_h, non_blocking=True)
+        self._step_body()
+        pos_h.copy_(self.pos, non_blocking=True)
+        vel_h.copy_(self.vel, non_blocking=True)
+        forces_h.copy_(self.ff.forces, non_blocking=True)
+        energy_h.copy_(self.ff.energy, non_blocking=True)
+
+    if not (self.use_graph and all(b.is_pinned() for b in bufs)):
+        self.pos.copy_(pos_h, non_blocking=True)
+        self.vel.copy_(vel_h, non_blocking=True)
+        self.ff.forces.copy_(forces_h, non_blocking=True)
+        self.step()
+        pos_h.copy_(self.pos, non_blocking=True)
+        vel_h.copy_(self.vel, non_blocking=True)
+        forces_h.copy_(self.ff.forces, non_blocking=True)
+        energy_h.copy_(self.ff.energy, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return
+    key = tuple(b.data_ptr() for b in bufs)
+    graphs = self.__dict__.setdefault("_host_graphs", {})
+    g = graphs.get(key)
+    if g is None:
+        if self.graph is None:
+            self._capture()          # warm-up (allocations, lazy module loads) happens there
+        torch.cuda.synchronize()
+        saved = (self.pos.clone(), self.vel.clone(), self.ff.forces.clone(), self.step_dev.clone())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        torch.cuda.synchronize()     # capture does not execute: device state and host buffers are untouched, restore anyway
+        self.pos.copy_(saved[0]); self.vel.copy_(saved[1]); self.ff.forces.copy_(saved[2]); self.step_dev.copy_(saved[3])
+        graphs[key] = g
+    g.replay()
     torch.cuda.current_stream().synchronize()
+    self.n_steps_done += 1
 
 
 LangevinEngine.step_host = _step_host

@@ -652,6 +652,35 @@ def test_langevin_trajectory_vs_reference_golden():
         assert rel_l2(eng.ke.cpu(), t["kinetic"][:, s]) < 1e-5
 
 
+def test_step_host_equals_device_resident_step():
+    """LangevinEngine.step_host (pinned host buffers, copies captured in the step graph) == LangevinEngine.step on the
+    device-resident state, bit for bit, over several steps (same Philox counters)."""
+    from flashmd.engine import LangevinEngine
+    g = load_golden("schnet_n54_b4.npz")
+    B, n = 4, 54
+    masses = torch.from_numpy(g["sys.masses"]).repeat(B)
+    v0 = torch.randn((B * n, 3), generator=torch.Generator().manual_seed(3)) * 0.3
+    outs = []
+    for host in (False, True):
+        ff, pos = _engine_from_golden(g, "w16a16", priors=True)
+        eng = LangevinEngine(ff, pos, v0, masses, torch.full((B,), 1.67), 0.004, 1.0, seed=11, use_graph=True)
+        if host:
+            ph, vh, fh = (torch.empty((B * n, 3)).pin_memory() for _ in range(3))
+            eh = torch.empty(B).pin_memory()
+            ph.copy_(eng.pos); vh.copy_(eng.vel); fh.copy_(ff.forces)
+            for _ in range(5):
+                eng.step_host(ph, vh, fh, eh)
+            outs.append((ph.clone(), vh.clone(), fh.clone(), eh.clone()))
+            assert torch.equal(ph, eng.pos.cpu()) and eng.n_steps_done == 5
+        else:
+            for _ in range(5):
+                eng.step()
+            torch.cuda.synchronize()
+            outs.append((eng.pos.cpu(), eng.vel.cpu(), ff.forces.cpu(), ff.energy.cpu()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def test_philox_noise_statistics_and_graph_replay():
     from flashmd import _lib as L
     from flashmd.engine import LangevinEngine
