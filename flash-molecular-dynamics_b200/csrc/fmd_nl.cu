@@ -274,49 +274,6 @@ nl_reverse_kernel(const int32_t* __restrict__ seg_ptr, const IdxT* __restrict__ 
   }
 }
 
-// ---------------------------------------------------------------- undirected pair list of the symmetric sorted list
-// pairs = edges with dst > src, in list order (so: sorted by the smaller bead, partner ascending).  Segments are sorted by
-// dst, so the edges of node i with dst > i are the tail of its segment.
-__global__ void __launch_bounds__(256)
-nl_pair_count_kernel(const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ dst, int n_nodes, int capacity,
-                     int32_t* __restrict__ cnt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_nodes) return;
-  const int E = min(seg_ptr[n_nodes], capacity);
-  int lo = min(seg_ptr[i], E);
-  const int end = min(seg_ptr[i + 1], E);
-  int hi = end;
-  while (lo < hi) {          // first edge of the segment with dst > i
-    const int mid = (lo + hi) >> 1;
-    if (dst[mid] > i) hi = mid; else lo = mid + 1;
-  }
-  cnt[i] = end - lo;
-}
-__global__ void __launch_bounds__(256)
-nl_pair_fill_kernel(const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
-                    const int32_t* __restrict__ rev, const float* __restrict__ dist, const int32_t* __restrict__ pair_ptr,
-                    int n_nodes, int capacity, int pair_capacity, int32_t* __restrict__ pair_own,
-                    int32_t* __restrict__ pair_nbr, float* __restrict__ pair_dist, int32_t* __restrict__ pidx) {
-  const int E = min(seg_ptr[n_nodes], capacity);
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-    const int i = src[e], j = dst[e];
-    // the pair is listed under its smaller bead `a`, as edge `f` of a's segment
-    const int a = j > i ? i : j;
-    const int f = j > i ? e : rev[e];
-    int p = -1;
-    if (f >= 0) {
-      const int first_hi = min(seg_ptr[a + 1], E) - (pair_ptr[a + 1] - pair_ptr[a]);
-      p = pair_ptr[a] + (f - first_hi);
-      if (j > i && p < pair_capacity) {
-        pair_own[p] = i;
-        pair_nbr[p] = j;
-        pair_dist[p] = dist[e];
-      }
-    }
-    pidx[e] = p;
-  }
-}
-
 // ---------------------------------------------------------------- generic CSR build
 template <typename IdxT>
 __global__ void __launch_bounds__(256) csr_hist(const IdxT* __restrict__ keys, int n, int num_nodes, int32_t* __restrict__ counts) {
@@ -420,26 +377,6 @@ extern "C" int fmd_nl_reverse(const int32_t* seg_ptr, const void* edge_src, cons
   else
     nl_reverse_kernel<int64_t><<<grid, 256, 0, st>>>(seg_ptr, (const int64_t*)edge_src, (const int64_t*)edge_dst,
                                                      n_nodes, capacity, (int64_t*)rev, nullptr, nullptr);
-  FMD_CHECK_LAUNCH();
-  return FMD_OK;
-}
-
-extern "C" int fmd_nl_pairs(const int32_t* seg_ptr, const int32_t* edge_src, const int32_t* edge_dst, const int32_t* rev,
-                            const float* dist, int n_nodes, int capacity, int pair_capacity, int32_t* pair_cnt,
-                            int32_t* pair_ptr, void* scan_workspace, int32_t* pair_own, int32_t* pair_nbr,
-                            float* pair_dist, int32_t* pidx, void* stream) {
-  FMD_REQUIRE(seg_ptr && edge_src && edge_dst && rev && dist && pair_cnt && pair_ptr && scan_workspace && pair_own &&
-                  pair_nbr && pair_dist && pidx, "fmd_nl_pairs: bad arguments");
-  if (n_nodes == 0) return FMD_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  nl_pair_count_kernel<<<fmd_div_up(n_nodes, 256), 256, 0, st>>>(seg_ptr, edge_dst, n_nodes, capacity, pair_cnt);
-  const int rc = fmd_exclusive_scan_i32(pair_cnt, pair_ptr, n_nodes, scan_workspace, stream);
-  if (rc != FMD_OK) return rc;
-  if (capacity > 0) {
-    const int grid = min(fmd_div_up(capacity, 256), fmd_num_sms() * 8);
-    nl_pair_fill_kernel<<<grid, 256, 0, st>>>(seg_ptr, edge_src, edge_dst, rev, dist, pair_ptr, n_nodes, capacity,
-                                              pair_capacity, pair_own, pair_nbr, pair_dist, pidx);
-  }
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

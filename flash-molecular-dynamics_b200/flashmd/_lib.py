@@ -52,8 +52,6 @@ _SIGS = {
                                      c_void_p, c_void_p], c_int),
     "fmd_edge_grad_to_forces_csr": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                      c_float, c_void_p, c_int, c_int, c_void_p], c_int),
-    "fmd_nl_pairs": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
-                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "fmd_nl_step": ([c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_int, c_void_p,
                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                      c_void_p], c_int),

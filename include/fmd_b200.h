@@ -107,7 +107,7 @@ int fmd_edge_grad_to_pos_atomic(const float* pos, const void* edge_src, const vo
 /* replaces: the same second half (kernels/cfconv_kernels.py:1696-1733), deterministic / atomic-free for the
  * sorted symmetric list of fmd_nl_fill:
  * out[i] = sign * sum_{e in seg(i)} (g_d[e] + g_d[rev[e]]) * u_e    (sign=+1 gives FORCES -dE/dx).
- * pair_mode != 0: `rev` is the edge -> pair map of fmd_nl_pairs and g_d the per-PAIR gradient, already summed over
+ * pair_mode != 0: `rev` is the edge -> pair map (pidx) of fmd_nl_step and g_d the per-PAIR gradient, already summed over
  * both directions (fmd_filter_cfconv_bwd): out[i] = sign * sum_e g_d[rev[e]] * u_e.
  * accumulate != 0 adds into out. int32 indices. */
 int fmd_edge_grad_to_forces_csr(const float* pos, const int32_t* seg_ptr, const int32_t* edge_dst,
@@ -138,23 +138,16 @@ int fmd_cfconv_grad_filter(const float* x, const float* g_out, const float* dist
                            int n_feat, float rc, void* g_filt, int ydt, const void* filt, int wdt,
                            float* g_dcut, int accumulate_dcut, void* stream);
 
-/* Undirected pair list of the sorted symmetric edge list (after fmd_nl_reverse): pairs = the edges with dst > src in
- * list order. The gradient of the energy with respect to a distance is needed only as the SUM over the two directions of
- * a pair (the filter depends on the distance alone: W(e) == W(rev e)), so the fused backward kernel runs over pairs - half
- * the tiles. No reference counterpart (the reference differentiates every directed edge).
- *   pair_cnt [n_nodes], pair_ptr [n_nodes+1] (pair_ptr[n_nodes] = number of pairs, stays on the device),
- *   scan_workspace as for fmd_exclusive_scan_i32; pair_own / pair_nbr / pair_dist [pair_capacity];
- *   pidx [capacity]: pair index of every directed edge (both directions of a pair map to it). */
-int fmd_nl_pairs(const int32_t* seg_ptr, const int32_t* edge_src, const int32_t* edge_dst, const int32_t* rev,
-                 const float* dist, int n_nodes, int capacity, int pair_capacity, int32_t* pair_cnt, int32_t* pair_ptr,
-                 void* scan_workspace, int32_t* pair_own, int32_t* pair_nbr, float* pair_dist, int32_t* pidx,
-                 void* stream);
-
 /* replaces: the per-step call of torch_cluster.radius_graph (neighbor_list/torch_impl.py:216-224) + build_csr_index /
  * build_src_csr_index (kernels/csr_kernels.py:88, 229) of the fused step, in FOUR launches: count (degrees and, if pair
  * outputs are given, the number of neighbours with a larger index), one launch that scans both count arrays, fill (edge
- * list + the undirected pair list of fmd_nl_pairs, written directly), reverse map (+ pidx).  Results identical to
- * fmd_nl_count / fmd_exclusive_scan_i32 / fmd_nl_fill / fmd_nl_reverse / fmd_nl_pairs (int32 indices).
+ * list + the undirected pair list), reverse map (+ pidx).  Edge list, seg_ptr, dist, rev identical to fmd_nl_count /
+ * fmd_exclusive_scan_i32 / fmd_nl_fill / fmd_nl_reverse (int32 indices).
+ * Undirected pair list (no reference counterpart: the reference differentiates every directed edge): pairs = the edges with
+ * dst > src in list order.  The gradient of the energy with respect to a distance is needed only as the SUM over the two
+ * directions of a pair (the filter depends on the distance alone: W(e) == W(rev e)), so the fused backward kernel runs over
+ * pairs - half the tiles.  pair_cnt [n_nodes], pair_ptr [n_nodes+1], pair_own / pair_nbr / pair_dist [pair_capacity],
+ * pidx [capacity]: pair index of every directed edge (both directions of a pair map to it).
  * seg_ptr[n_nodes] / pair_ptr[n_nodes] hold the live edge / pair counts on the device.  pair_cnt == NULL: no pair list. */
 int fmd_nl_step(const float* pos, const int32_t* mol_ptr, int n_mols, int n_nodes, int max_mol_size, float rc,
                 int max_num_neighbors, int32_t* deg, int32_t* seg_ptr, int capacity, int32_t* edge_src,

@@ -39,7 +39,7 @@ def test_every_entry_point_cites_the_reference_interface_it_replaces():
     assert len(blocks) >= 25
     uncited = [n for c, n in blocks if "replaces" not in c and "contract as" not in c and "Same physics" not in c
                and n not in ("fmd_version", "fmd_sm_count", "fmd_exclusive_scan_i32", "fmd_increment_u64",
-                             "fmd_philox_normal", "fmd_nl_fill", "fmd_nl_reverse", "fmd_nl_pairs", "fmd_debug_set_trace_fwd",
+                             "fmd_philox_normal", "fmd_nl_fill", "fmd_nl_reverse", "fmd_debug_set_trace_fwd",
                              "fmd_debug_set_trace_bwd")]
     assert not uncited, uncited
 
