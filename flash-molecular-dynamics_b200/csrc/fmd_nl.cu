@@ -112,7 +112,7 @@ nl_kernel(const float* __restrict__ pos, const int32_t* __restrict__ mol_ptr, fl
 // out[n] = total.  n is a few 10^4: one CTA per array is faster than the three-kernel scan (three launches per array).
 __global__ void __launch_bounds__(1024)
 scan2_kernel(const int32_t* __restrict__ in0, int32_t* __restrict__ out0, const int32_t* __restrict__ in1,
-             int32_t* __restrict__ out1, int n) {
+             int32_t* __restrict__ out1, int n, int32_t* __restrict__ max_total0) {
   const int32_t* in = blockIdx.x == 0 ? in0 : in1;
   int32_t* out = blockIdx.x == 0 ? out0 : out1;
   if (!in || !out) return;
@@ -154,7 +154,11 @@ scan2_kernel(const int32_t* __restrict__ in0, int32_t* __restrict__ out0, const 
     if (threadIdx.x == 1023) carry_s = run;
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[n] = carry_s;
+  if (threadIdx.x == 0) {
+    out[n] = carry_s;
+    // sticky high-water mark of the edge count (capacity overflows between two host checks are not missed)
+    if (blockIdx.x == 0 && max_total0 && carry_s > *max_total0) *max_total0 = carry_s;
+  }
 }
 
 // ---------------------------------------------------------------- exclusive scan (3 phases)
@@ -385,7 +389,7 @@ extern "C" int fmd_nl_step(const float* pos, const int32_t* mol_ptr, int n_mols,
                            int max_num_neighbors, int32_t* deg, int32_t* seg_ptr, int capacity, int32_t* edge_src,
                            int32_t* edge_dst, float* dist, int32_t* rev, int32_t* pair_cnt, int32_t* pair_ptr,
                            int pair_capacity, int32_t* pair_own, int32_t* pair_nbr, float* pair_dist, int32_t* pidx,
-                           void* stream) {
+                           int32_t* max_edges, void* stream) {
   FMD_REQUIRE(pos && mol_ptr && deg && seg_ptr && edge_src && edge_dst && dist && rev, "fmd_nl_step: null argument");
   const bool pairs = pair_cnt != nullptr;
   FMD_REQUIRE(!pairs || (pair_ptr && pair_own && pair_nbr && pair_dist && pidx), "fmd_nl_step: incomplete pair outputs");
@@ -398,7 +402,7 @@ extern "C" int fmd_nl_step(const float* pos, const int32_t* mol_ptr, int n_mols,
   pc.deg_hi = pairs ? pair_cnt : nullptr;
   nl_kernel<false, int32_t><<<grid, NL_WARPS * 32, 0, st>>>(pos, mol_ptr, rc2, max_num_neighbors + 1, deg, nullptr, 0,
                                                             nullptr, nullptr, nullptr, pc);
-  scan2_kernel<<<pairs ? 2 : 1, 1024, 0, st>>>(deg, seg_ptr, pair_cnt, pair_ptr, n_nodes);
+  scan2_kernel<<<pairs ? 2 : 1, 1024, 0, st>>>(deg, seg_ptr, pair_cnt, pair_ptr, n_nodes, max_edges);
   NlPairs pf{};
   if (pairs) {
     pf.pair_ptr = pair_ptr;

@@ -54,7 +54,7 @@ _SIGS = {
                                      c_float, c_void_p, c_int, c_int, c_void_p], c_int),
     "fmd_nl_step": ([c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_int, c_void_p,
                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                     c_void_p], c_int),
+                     c_void_p, c_void_p], c_int),
     "fmd_cfconv_csr": ([c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                         c_int, c_float, c_void_p, c_void_p], c_int),
     "fmd_cfconv_grad_filter": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,

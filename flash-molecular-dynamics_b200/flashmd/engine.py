@@ -335,6 +335,7 @@ class ForceField:
         self.deg = torch.zeros(N, dtype=i32, device=dev)
         self.seg_ptr = torch.zeros(N + 1, dtype=i32, device=dev)
         self.n_edges_dev = self.seg_ptr[N:]                      # int32[1] view: live edge count
+        self.max_edges_dev = torch.zeros(1, dtype=i32, device=dev)    # sticky high-water mark (fused path: fmd_nl_step)
         self.scan_ws = torch.zeros(N // 1024 + 4, dtype=i32, device=dev)
         self.src = torch.zeros(cap, dtype=i32, device=dev)
         self.dst = torch.zeros(cap, dtype=i32, device=dev)
@@ -458,7 +459,7 @@ class ForceField:
             L.call("fmd_nl_step", L.ptr(pos), L.ptr(self.mol_ptr), self.B, self.N, self.max_mol, w.cutoff, self.max_nn,
                    L.ptr(self.deg), L.ptr(self.seg_ptr), self.cap, L.ptr(self.src), L.ptr(self.dst), L.ptr(self.dist),
                    L.ptr(self.rev), L.ptr(self.pair_cnt), L.ptr(self.pair_ptr), self.pair_cap, L.ptr(self.pair_own),
-                   L.ptr(self.pair_nbr), L.ptr(self.pair_dist), L.ptr(self.pidx), st)
+                   L.ptr(self.pair_nbr), L.ptr(self.pair_dist), L.ptr(self.pidx), L.ptr(self.max_edges_dev), st)
             self._n += 4
             return
         L.call("fmd_nl_count", L.ptr(pos), L.ptr(self.mol_ptr), self.B, self.N, self.max_mol, w.cutoff, self.max_nn,

@@ -283,8 +283,12 @@ class _Simulation:
         if self.engine is not None:
             # fused path: nothing here waits for the GPU
             eng = self.engine
-            status = torch.stack([spread.max(), torch.isnan(spread).any().float(),
-                                  eng.ff.n_edges_dev[0].float() if eng.ff.w is not None else spread.new_zeros(())])
+            # edge count: the larger of the live count and the high-water mark since the run began (an overflow between two
+            # save points is not missed)
+            n_e = spread.new_zeros(())
+            if eng.ff.w is not None:
+                n_e = torch.maximum(eng.ff.n_edges_dev[0], eng.ff.max_edges_dev[0]).float()
+            status = torch.stack([spread.max(), torch.isnan(spread).any().float(), n_e])
             tensors = {"pos": x, "status": status}
             if self.save_forces:
                 tensors["forces"] = forces.view(-1, self.n_atoms, self.n_dims)

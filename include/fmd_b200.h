@@ -148,11 +148,13 @@ int fmd_cfconv_grad_filter(const float* x, const float* g_out, const float* dist
  * directions of a pair (the filter depends on the distance alone: W(e) == W(rev e)), so the fused backward kernel runs over
  * pairs - half the tiles.  pair_cnt [n_nodes], pair_ptr [n_nodes+1], pair_own / pair_nbr / pair_dist [pair_capacity],
  * pidx [capacity]: pair index of every directed edge (both directions of a pair map to it).
- * seg_ptr[n_nodes] / pair_ptr[n_nodes] hold the live edge / pair counts on the device.  pair_cnt == NULL: no pair list. */
+ * seg_ptr[n_nodes] / pair_ptr[n_nodes] hold the live edge / pair counts on the device.  pair_cnt == NULL: no pair list.
+ * max_edges (nullable, int32[1]): sticky high-water mark, max_edges[0] = max(max_edges[0], edge count of this call): a host
+ * that checks the capacity only now and then (the kernels clamp, they never write out of bounds) does not miss an overflow. */
 int fmd_nl_step(const float* pos, const int32_t* mol_ptr, int n_mols, int n_nodes, int max_mol_size, float rc,
                 int max_num_neighbors, int32_t* deg, int32_t* seg_ptr, int capacity, int32_t* edge_src,
                 int32_t* edge_dst, float* dist, int32_t* rev, int32_t* pair_cnt, int32_t* pair_ptr, int pair_capacity,
-                int32_t* pair_own, int32_t* pair_nbr, float* pair_dist, int32_t* pidx, void* stream);
+                int32_t* pair_own, int32_t* pair_nbr, float* pair_dist, int32_t* pidx, int32_t* max_edges, void* stream);
 
 /* ---------------------------------------------------------------- fused filter network (x) CFConv (tensor cores) */
 

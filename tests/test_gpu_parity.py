@@ -108,11 +108,12 @@ def test_fused_step_neighbor_and_pair_list_bit_exact(case):
     pcnt, pptr = torch.zeros(N, **i32), torch.zeros(N + 1, **i32)
     pown, pnbr = torch.full((pcap,), -7, **i32), torch.full((pcap,), -7, **i32)
     pdist = torch.zeros(pcap, device=DEV)
+    hwm = torch.full((1,), 3, **i32)
     L.call("fmd_nl_step", L.ptr(posd), L.ptr(mol_ptr), len(case["sizes"]), N, max(case["sizes"]), case["rc"], 1000,
            L.ptr(deg), L.ptr(seg), cap, L.ptr(src), L.ptr(dst), L.ptr(dist), L.ptr(rev), L.ptr(pcnt), L.ptr(pptr), pcap,
-           L.ptr(pown), L.ptr(pnbr), L.ptr(pdist), L.ptr(pidx), L.stream_ptr())
+           L.ptr(pown), L.ptr(pnbr), L.ptr(pdist), L.ptr(pidx), L.ptr(hwm), L.stream_ptr())
     torch.cuda.synchronize()
-    assert int(seg[N]) == E
+    assert int(seg[N]) == E and int(hwm[0]) == max(E, 3)          # sticky high-water mark of the edge count
     np.testing.assert_array_equal(torch.stack([src[:E], dst[:E]]).cpu().numpy().astype(np.int64), ref)
     sptr, _ = O.build_csr(ref[0], N)
     np.testing.assert_array_equal(seg.cpu().numpy().astype(np.int64), sptr)
@@ -598,6 +599,13 @@ def test_edge_capacity_and_large_batch_properties():
     ei = torch.from_numpy(O.radius_graph(p0.numpy(), np.array([0, n]), sysd["cutoff"]))
     e0, f0 = O.schnet_energy_forces(P.to(torch.float64), p0.double(), types[:n].cpu(), torch.zeros(n, dtype=torch.long), 1, ei)
     assert rel_l2(f[:n].cpu(), f0) < 1e-5 and rel_l2(e[:1].cpu(), e0) < 1e-5
+    # an edge capacity that is too small: the kernels clamp (no out-of-bounds write, finite results) and the overflow stays
+    # visible in the sticky high-water mark even after the list has shrunk below the capacity again
+    small = ForceField(w, [], types, ptr, precision="w16a16", edge_capacity=E // 2)
+    e_s, f_s = small.compute(pos)
+    assert bool(torch.isfinite(f_s).all()) and int(small.n_edges_dev[0]) == E and int(small.max_edges_dev[0]) == E > small.cap
+    small.compute(pos * 3.0)           # expanded: far fewer edges
+    assert int(small.n_edges_dev[0]) < small.cap and int(small.max_edges_dev[0]) == E
 
 
 def test_cfg5_shape_500_beads_5_blocks_vs_oracle():
