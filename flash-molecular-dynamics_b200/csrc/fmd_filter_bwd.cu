@@ -307,6 +307,19 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
       const uint4* a_own = reinterpret_cast<const uint4*>(a + (size_t)own * NF);
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
+        // The owner rows (broadcast global loads, 64 + 64 bytes per slot) are a first touch in L1 for every slot: their L2
+        // round trip was ~37 % of this role's time (ncu: long scoreboard on the first multiply).  They are issued first,
+        // and the refill copies of the PREVIOUS slot (8 cp.async, ~55 issue cycles each) go out under that latency.
+        uint4 gi[4], ai[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          gi[c] = __ldg(gm_own + q * 4 + c);
+          ai[c] = __ldg(a_own + q * 4 + c);
+        }
+        if (q > 0) {
+          if (has_next) issue_slot(i + 1, q - 1);   // the slot consumed last takes the same features of the next tile
+          cp_async_commit();
+        }
         cp_async_wait<3>();          // slot q of this tile (committed 4 groups ago) has landed ...
         __syncwarp();                // ... for every lane of this warp (the rows are private to the warp)
         const uint8_t* row = smem + BO_AS + q * (TILE * 128) + e * 128;
@@ -315,17 +328,15 @@ filter_cfconv_bwd_kernel(const float* __restrict__ dist, const int32_t* __restri
         for (int c = 0; c < 4; ++c) {
           const uint4 aj = *reinterpret_cast<const uint4*>(row + ((((uint32_t)c) ^ e7) << 4));
           const uint4 gj = *reinterpret_cast<const uint4*>(row + ((((uint32_t)(4 + c)) ^ e7) << 4));
-          const uint4 gi = __ldg(gm_own + q * 4 + c);
-          const uint4 ai = __ldg(a_own + q * 4 + c);
-          r[4 * c + 0] = hfma2_u32(aj.x, gi.x, hmul2_u32(gj.x, ai.x));
-          r[4 * c + 1] = hfma2_u32(aj.y, gi.y, hmul2_u32(gj.y, ai.y));
-          r[4 * c + 2] = hfma2_u32(aj.z, gi.z, hmul2_u32(gj.z, ai.z));
-          r[4 * c + 3] = hfma2_u32(aj.w, gi.w, hmul2_u32(gj.w, ai.w));
+          r[4 * c + 0] = hfma2_u32(aj.x, gi[c].x, hmul2_u32(gj.x, ai[c].x));
+          r[4 * c + 1] = hfma2_u32(aj.y, gi[c].y, hmul2_u32(gj.y, ai[c].y));
+          r[4 * c + 2] = hfma2_u32(aj.z, gi[c].z, hmul2_u32(gj.z, ai[c].z));
+          r[4 * c + 3] = hfma2_u32(aj.w, gi[c].w, hmul2_u32(gj.w, ai[c].w));
         }
         tmem_st16(tmem + TM_GW + s * 64 + lane_sel + q * 16, r);
-        if (has_next) issue_slot(i + 1, q);      // the slot just consumed takes the same features of the next tile
-        cp_async_commit();
       }
+      if (has_next) issue_slot(i + 1, 3);
+      cp_async_commit();
       tmem_st_wait();
       fence_before_sync();
       __syncwarp();
