@@ -1,7 +1,11 @@
-// Classical prior terms, owner-computes form: one warp per bead walks the bead's incident terms
-// (static topology, CSR built once at set-up) and accumulates the bead's force and its share of the
+// Classical prior terms, owner-computes form: eight lanes per bead walk the bead's incident terms
+// (static topology, CSR built once at set-up) and accumulate the bead's force and its share of the
 // term energies.  No atomics, deterministic; replaces the term-parallel atomicAdd kernel on the step
 // path (which serialised ~36 k repulsion pairs per molecule onto one energy address).
+// The kernel is bound by the latency of its dependent load chains (incidence record -> term indices ->
+// positions -> parameters), not by arithmetic or bandwidth: measured on the benchmark system, a warp per
+// bead at 48 registers took 83 us; 32 registers (64 resident warps per SM) 67 us; four beads per warp 53 us
+// (17 us without the repulsion pairs); shared-memory staging of the positions made it slower.
 //
 // Math per term (reference file:line):
 //   bonds      k (d - x0)^2 + V0          prior/harmonic.py:122-123, geometry/internal_coordinates.py:73-101
@@ -38,12 +42,19 @@ __device__ __forceinline__ V3 cross(V3 a, V3 b) {
 }
 
 constexpr int WARPS = 8;
+#ifndef FMD_PRIOR_LPB
+#define FMD_PRIOR_LPB 8
+#endif
+constexpr int LPB = FMD_PRIOR_LPB;     // lanes per bead
 
 // PACKED: two-body records are 8 bytes {other | kind << 28, parameter id} and the parameters (k, x0, V0 | sigma) come
 // from a small deduplicated float4 table (a few hundred type pairs: L1-resident) - the 16-byte records were 147 MB of
 // HBM traffic per step at 128 x 269 beads, by far the largest stream outside the two fused edge kernels.
+#ifndef FMD_PRIOR_MIN_CTAS
+#define FMD_PRIOR_MIN_CTAS 8
+#endif
 template <bool PACKED>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, FMD_PRIOR_MIN_CTAS)
 prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __restrict__ pair_ptr,
                  const void* __restrict__ pair_ent_v, const float4* __restrict__ pair_tab,
                  const int32_t* __restrict__ mb_ptr,
@@ -53,17 +64,20 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
                  const float* __restrict__ dih_k2, const float* __restrict__ dih_v0, int n_degs,
                  const int32_t* __restrict__ imp_map, int n_imp, const float4* __restrict__ imp_par,
                  float* __restrict__ e_atom, float* __restrict__ forces, int accumulate_forces) {
-  const int lane = threadIdx.x & 31;
-  const int a = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (a >= n_nodes) return;
+  // LPB lanes per bead: the kernel is bound by the latency of its dependent load chains (record -> index -> position), so
+  // a warp works on 32 / LPB beads at once instead of one
+  const int lane = threadIdx.x & (LPB - 1);
+  const int a_raw = (blockIdx.x * (WARPS * 32) + threadIdx.x) / LPB;
+  const bool valid = a_raw < n_nodes;          // no early exit: the lane reductions below use the full-warp mask
+  const int a = valid ? a_raw : n_nodes - 1;
   const V3 pa = ld3(pos, a);
   V3 f = {0.f, 0.f, 0.f};
   float e = 0.f;
   // ---- two-body terms: entry = {other | kind << 28, p0, p1, p2}
-  if (pair_ptr) {
+  if (pair_ptr && valid) {
     const int p1 = __ldg(&pair_ptr[a + 1]);
 #pragma unroll 8   // independent record -> position load chains in flight (the loop is latency-bound on the record stream)
-    for (int p = __ldg(&pair_ptr[a]) + lane; p < p1; p += 32) {
+    for (int p = __ldg(&pair_ptr[a]) + lane; p < p1; p += LPB) {
       int head, tab_id = 0;
       float q0, q1, q2, q3 = 0.f;
       if (PACKED) {
@@ -97,9 +111,9 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
     }
   }
   // ---- three- and four-body terms: entry = term | role << 28 | is_dihedral << 30
-  if (mb_ptr) {
+  if (mb_ptr && valid) {
     const int q1 = __ldg(&mb_ptr[a + 1]);
-    for (int q = __ldg(&mb_ptr[a]) + lane; q < q1; q += 32) {
+    for (int q = __ldg(&mb_ptr[a]) + lane; q < q1; q += LPB) {
       const int ent = __ldg(&mb_ent[q]);
       const int t = ent & 0x0FFFFFFF, role = (ent >> 28) & 3, table = (int)((unsigned)ent >> 30);
       if (table == 0) {
@@ -142,18 +156,25 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
                  b3 = sub(ld3(pos, l), ld3(pos, k_));
         const V3 m = cross(b1, b2), n = cross(b2, b3);
         const float b2sq = dot(b2, b2), nb2 = sqrtf(b2sq);
-        const float phi = atan2f(nb2 * dot(b1, n), dot(m, n));
+        const float ys = nb2 * dot(b1, n), xc = dot(m, n);      // phi = atan2(ys, xc)
         float dEdphi = 0.f, et;
         if (table == 1) {
+          // Fourier series in phi without a trigonometric call: (cos phi, sin phi) = (xc, ys) / |(xc, ys)|, the higher
+          // harmonics by the angle-addition recurrence (the reference evaluates sin / cos of n * atan2(ys, xc))
+          const float inv_r = rsqrtf(fmaxf(xc * xc + ys * ys, 1e-30f));
+          const float c1 = xc * inv_r, s1 = ys * inv_r;
+          float c = c1, sn = s1;
           et = dih_v0 ? __ldg(&dih_v0[t]) : 0.f;
           for (int d = 0; d < n_degs; ++d) {
-            float s, c;
-            sincosf((float)(d + 1) * phi, &s, &c);
             const float k1 = __ldg(&dih_k1[(size_t)t * n_degs + d]), k2 = __ldg(&dih_k2[(size_t)t * n_degs + d]);
-            et += k1 * s + k2 * c;
-            dEdphi += (float)(d + 1) * (k1 * c - k2 * s);
+            et += k1 * sn + k2 * c;
+            dEdphi += (float)(d + 1) * (k1 * c - k2 * sn);
+            const float cn = c * c1 - sn * s1;
+            sn = sn * c1 + c * s1;
+            c = cn;
           }
         } else {
+          const float phi = atan2f(ys, xc);
           const float4 pp = __ldg(&imp_par[t]);     // {k, x0, V0, form}
           float x = phi;
           if (__float_as_int(pp.w) == FMD_IMPROPER_SHIFTED) x = (phi < 0.f ? phi + 2.0f * FMD_PI_F : phi) - FMD_PI_F;
@@ -173,11 +194,14 @@ prior_csr_kernel(const float* __restrict__ pos, int n_nodes, const int32_t* __re
       }
     }
   }
-  f.x = warp_sum(f.x);
-  f.y = warp_sum(f.y);
-  f.z = warp_sum(f.z);
-  e = warp_sum(e);
-  if (lane == 0) {
+#pragma unroll
+  for (int o = LPB / 2; o > 0; o >>= 1) {      // fixed butterfly order within the bead's lanes: deterministic
+    f.x += __shfl_xor_sync(0xffffffffu, f.x, o);
+    f.y += __shfl_xor_sync(0xffffffffu, f.y, o);
+    f.z += __shfl_xor_sync(0xffffffffu, f.z, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+  }
+  if (lane == 0 && valid) {
     if (accumulate_forces) {
       forces[3 * a + 0] += f.x;
       forces[3 * a + 1] += f.y;
@@ -205,7 +229,7 @@ extern "C" int fmd_priors_csr(const float* pos, int n_nodes, const int32_t* pair
   FMD_REQUIRE(n_dih == 0 || (dih_map && dih_k1 && dih_k2), "fmd_priors_csr: missing dihedral tables");
   FMD_REQUIRE(n_imp == 0 || (imp_map && imp_par), "fmd_priors_csr: missing improper tables");
   if (n_nodes <= 0) return FMD_OK;
-  const int grid = fmd_div_up(n_nodes, WARPS);
+  const int grid = fmd_div_up(n_nodes, WARPS * 32 / LPB);
   if (pair_tab)
     prior_csr_kernel<true><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
         pos, n_nodes, pair_ptr, pair_ent, (const float4*)pair_tab, mb_ptr, mb_ent, ang_map, n_ang, (const float4*)ang_par,
