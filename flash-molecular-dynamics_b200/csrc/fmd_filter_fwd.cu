@@ -470,28 +470,37 @@ filter_cfconv_fwd_kernel(const float* __restrict__ dist, const int32_t* __restri
 }
 
 // out[i] = 0 for empty segments; out[i] += head partials of the later tiles a straddling segment touches,
-// in tile order (deterministic).  One warp per node, float4 per lane (NF = 128).
+// in tile order (deterministic).  Eight lanes per node, four float4 per lane (NF = 128): the kernel is a chain of dependent
+// loads (segment bounds -> rows), so a warp works on four nodes at once.
 __global__ void __launch_bounds__(256)
 cfconv_fixup_kernel(const int32_t* __restrict__ seg_ptr, int n_nodes, int capacity, const float* __restrict__ part,
                     float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 7;
+  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   if (node >= n_nodes) return;
   const int E = min(capacity, __ldg(&seg_ptr[n_nodes]));
   const int s0 = min(__ldg(&seg_ptr[node]), E), s1 = min(__ldg(&seg_ptr[node + 1]), E);
   float4* o = reinterpret_cast<float4*>(out + (size_t)node * NF) + lane;
   if (s1 <= s0) {
-    *o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[8 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
   const int t0 = s0 / TILE, t1 = (s1 - 1) / TILE;
   if (t1 == t0) return;
-  float4 v = *o;
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = o[8 * k];
   for (int t = t0 + 1; t <= t1; ++t) {
-    const float4 p = __ldg(reinterpret_cast<const float4*>(part + (size_t)t * NF) + lane);
-    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    const float4* pr = reinterpret_cast<const float4*>(part + (size_t)t * NF) + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 p = __ldg(pr + 8 * k);
+      v[k].x += p.x; v[k].y += p.y; v[k].z += p.z; v[k].w += p.w;
+    }
   }
-  *o = v;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[8 * k] = v[k];
 }
 
 }  // namespace
@@ -529,7 +538,7 @@ extern "C" int fmd_filter_cfconv_fwd(const float* dist, const int32_t* edge_owne
                                               (const __half*)x_h, out, part, g_fwd_trace);
     FMD_CHECK_LAUNCH();
   }
-  cfconv_fixup_kernel<<<fmd_div_up((long long)n_nodes * 32, 256), 256, 0, st>>>(seg_ptr, n_nodes, capacity, part, out);
+  cfconv_fixup_kernel<<<fmd_div_up((long long)n_nodes * 8, 256), 256, 0, st>>>(seg_ptr, n_nodes, capacity, part, out);
   FMD_CHECK_LAUNCH();
   return FMD_OK;
 }

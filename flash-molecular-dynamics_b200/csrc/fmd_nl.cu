@@ -254,6 +254,14 @@ nl_reverse_kernel(const int32_t* __restrict__ seg_ptr, const IdxT* __restrict__ 
   const int E = min(seg_ptr[n_nodes], capacity);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
     const int s = (int)src[e], t = (int)dst[e];
+    if (pidx && t > s) {
+      // fused step (pidx given: the list is symmetric, the engine refuses lists that max_num_neighbors can truncate): this
+      // edge is a pair's first direction, its pair index needs no search; rev of BOTH directions is written by the thread
+      // of the mirror edge below, so only half of the threads walk a binary search
+      const int first_hi = min(seg_ptr[s + 1], E) - (pair_ptr[s + 1] - pair_ptr[s]);
+      pidx[e] = pair_ptr[s] + (e - first_hi);
+      continue;
+    }
     int lo = seg_ptr[t], hi = min(seg_ptr[t + 1], E);
     int found = -1;
     while (lo < hi) {
@@ -265,13 +273,13 @@ nl_reverse_kernel(const int32_t* __restrict__ seg_ptr, const IdxT* __restrict__ 
     }
     rev[e] = (IdxT)found;
     if (pidx) {
-      // the pair is listed under its smaller bead `a`, as edge `f` of a's segment; the pairs of a are the tail of the segment
-      const int a = t > s ? s : t;
-      const int f = t > s ? e : found;
+      // t < s: the pair is listed under the smaller bead t, as edge `found` of t's segment (the pairs of t are the tail of
+      // its segment)
       int p = -1;
-      if (f >= 0) {
-        const int first_hi = min(seg_ptr[a + 1], E) - (pair_ptr[a + 1] - pair_ptr[a]);
-        p = pair_ptr[a] + (f - first_hi);
+      if (found >= 0) {
+        rev[found] = (IdxT)e;
+        const int first_hi = min(seg_ptr[t + 1], E) - (pair_ptr[t + 1] - pair_ptr[t]);
+        p = pair_ptr[t] + (found - first_hi);
       }
       pidx[e] = p;
     }
