@@ -117,14 +117,22 @@ edge_grad_to_forces_csr_kernel(const float* __restrict__ pos, const int32_t* __r
                                const int32_t* __restrict__ dst, const int32_t* __restrict__ rev,
                                const float* __restrict__ dist, const float* __restrict__ g_d, int n_nodes, int n_edges,
                                float sign, float* __restrict__ out, int accumulate, int pair_mode) {
-  const int lane = threadIdx.x & 31;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int i = wid; i < n_nodes; i += nw) {
-    const int a = min(seg_ptr[i], n_edges), b = min(seg_ptr[i + 1], n_edges);
+  // eight lanes per node (four nodes per warp): the kernel is a chain of dependent loads (segment bounds -> edge record ->
+  // pair gradient / partner position), so more nodes in flight per warp is what it needs; every lane runs the same number of
+  // iterations of the outer loop (uniform bound), the lane reduction uses the full-warp mask
+  const int lane = threadIdx.x & 7;
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int ng = (gridDim.x * blockDim.x) >> 3;
+  const int n_iter = (n_nodes + ng - 1) / ng;
+  for (int it = 0; it < n_iter; ++it) {
+    const int i_raw = gid + it * ng;
+    const bool valid = i_raw < n_nodes;
+    const int i = valid ? i_raw : n_nodes - 1;
+    const int a = min(seg_ptr[i], n_edges), b = valid ? min(seg_ptr[i + 1], n_edges) : a;
     const float px = pos[3 * i + 0], py = pos[3 * i + 1], pz = pos[3 * i + 2];
     float fx = 0.f, fy = 0.f, fz = 0.f;
-    for (int e = a + lane; e < b; e += 32) {
+#pragma unroll 4
+    for (int e = a + lane; e < b; e += 8) {
       const int j = dst[e];
       const int r = rev[e];
       float g;
@@ -139,10 +147,13 @@ edge_grad_to_forces_csr_kernel(const float* __restrict__ pos, const int32_t* __r
       fy += g * (pos[3 * j + 1] - py);
       fz += g * (pos[3 * j + 2] - pz);
     }
-    fx = warp_sum(fx);
-    fy = warp_sum(fy);
-    fz = warp_sum(fz);
-    if (lane == 0) {
+#pragma unroll
+    for (int o_ = 4; o_ > 0; o_ >>= 1) {
+      fx += __shfl_xor_sync(0xffffffffu, fx, o_);
+      fy += __shfl_xor_sync(0xffffffffu, fy, o_);
+      fz += __shfl_xor_sync(0xffffffffu, fz, o_);
+    }
+    if (lane == 0 && valid) {
       float* o = out + 3 * (size_t)i;
       if (accumulate) {
         o[0] += sign * fx;
@@ -503,7 +514,7 @@ extern "C" int fmd_edge_grad_to_forces_csr(const float* pos, const int32_t* seg_
                                            void* stream) {
   FMD_REQUIRE(pos && seg_ptr && edge_dst && rev && dist && g_d && out, "fmd_edge_grad_to_forces_csr: bad arguments");
   if (n_nodes == 0) return FMD_OK;
-  const int grid = min(fmd_div_up((long long)n_nodes * 32, 256), fmd_num_sms() * 16);
+  const int grid = min(fmd_div_up((long long)n_nodes * 8, 256), fmd_num_sms() * 16);
   edge_grad_to_forces_csr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, seg_ptr, edge_dst, rev, dist, g_d,
                                                                          n_nodes, n_edges, sign, out, accumulate, pair_mode);
   FMD_CHECK_LAUNCH();
